@@ -1,0 +1,132 @@
+/*
+ * plmc_b200.h -- C ABI of libplmc_b200.so, the sm_100a (B200) engine behind the
+ * projected-LMC marginal-likelihood / prediction path.
+ *
+ * The reference (QWERTY6191/projected-lmc) has no FFI: its hot path is Python
+ * that reaches torch/gpytorch/linear_operator kernels.  Each entry point below
+ * names the reference call site (file:line under the reference checkout) whose
+ * arithmetic it replaces; INTEGRATION.md shows the ctypes binding.
+ *
+ * Contract:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     the parameter name ends in _host;
+ *   - the caller owns every buffer, including workspaces; the library never
+ *     allocates, frees or synchronises; all work is ordered on `stream`
+ *     (a cudaStream_t passed as void*);
+ *   - return value: 0 ok, -1 bad argument, -2 launch failure.  Numerical
+ *     failure (non-PD matrix) is reported LAPACK-style in a device `info`
+ *     array, never through the return code;
+ *   - re-entrant, no global mutable state beyond one-time function attributes;
+ *   - FP64 throughout; matrices row-major; "npad" = n rounded up to 128.
+ */
+#ifndef PLMC_B200_H
+#define PLMC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLMC_KERNEL_RBF 0      /* exp(-s/2)                               */
+#define PLMC_KERNEL_MATERN52 1 /* (1+sqrt5 r+5/3 r^2) exp(-sqrt5 r)       */
+#define PLMC_KERNEL_MATERN32 2 /* (1+sqrt3 r) exp(-sqrt3 r)               */
+#define PLMC_KERNEL_MATERN12 3 /* exp(-r)                                 */
+
+int plmc_version(void);
+/* one-time per device: opt in to >48 KB dynamic shared memory for the kernels */
+int plmc_init(void);
+/* npad for a problem of order n (multiple of 128) */
+long long plmc_npad(long long n);
+/* bytes of the Dinv side buffer potrf needs for `batch` matrices of order npad */
+long long plmc_dinv_bytes(long long npad, int batch);
+
+/* ---- (1) projection: ProjectedGPModel.project_data, projected_lmc.py:1014-1021
+ * TY[l, i] = sum_t T[t, l] * Y[i, t]   (T = projection_matrix(), :1003-1012)
+ * Y [n, p] row-major, T [p, q] row-major, TY [q, ldty] (ldty >= n).            */
+int plmc_project_fwd(const double* Y, const double* T, double* TY, long long n, int p, int q, long long ldty,
+                     void* stream);
+/* dT[t, l] = sum_i Y[i, t] * G[l, i]  (autograd of the matmuls at :1016-1019).
+ * partial: workspace of plmc_project_bwd_ws(n,p,q) bytes.                       */
+long long plmc_project_bwd_ws(long long n, int p, int q);
+int plmc_project_bwd(const double* Y, const double* G, long long ldg, double* dT, double* partial, long long n,
+                     int p, int q, void* stream);
+
+/* ---- (2) Gram build: handle_covar_ kernels, projected_lmc.py:151-167, evaluated
+ * at :1201; gpytorch sq_dist semantics (centre by column mean, expansion,
+ * clamp_min 0), ScaleKernel and the GaussianLikelihood diagonal (:1200).       */
+/* xmean[k] = mean_i X[i,k] */
+int plmc_col_mean(const double* X, long long n, int d, double* xmean, void* stream);
+/* Z[l, i, k] = (X[i,k]-xmean[k]) / ell[l,k], zero padded to [q, rows_pad, dpad];
+ * zn[l, i] = sum_k Z^2.  dpad % 4 == 0, rows_pad >= n.                          */
+int plmc_scale_inputs(const double* X, const double* xmean, const double* ell, double* Z, double* zn, long long n,
+                      int d, int dpad, long long rows_pad, int q, void* stream);
+/* K[l] (lower 128-tiles of a [npad, ld] matrix) = os[l]*k(s_ij) + diag_add[l]*I,
+ * identity in the padding.  os may be NULL (no ScaleKernel).                    */
+int plmc_gram(const double* Z, const double* zn, int kernel_id, const double* os, const double* diag_add, double* K,
+              long long ld, long long stride, long long n, long long npad, int dpad, int q, void* stream);
+/* Kx[l, i, j] = os[l]*k(train_i, test_j): [q, npad, ldx] with ldx >= mt, mt%128==0;
+ * rows >= n are zero.                                                            */
+int plmc_cross_gram(const double* Ztrain, const double* zntrain, const double* Ztest, const double* zntest,
+                    int kernel_id, const double* os, double* Kx, long long ldx, long long stride, long long n,
+                    long long npad, long long mt_rows_pad, long long mt, int dpad, int q, void* stream);
+
+/* ---- (3) factorisation: MultivariateNormal.log_prob -> psd_safe_cholesky,
+ * triangular solve, logdet (gpytorch; reached from projected_lmc.py:1201).     */
+int plmc_potrf_batched(double* K, long long ld, long long stride, long long npad, int batch, double* dinv, int* info,
+                       void* stream);
+/* op: 0 X L^T = aB (B m x npad) | 1 X L = aB | 2 L X = aB (B npad x m) | 3 L^T X = aB ; m % 128 == 0 */
+int plmc_trsm_batched(int op, const double* L, long long ld, long long stride, long long npad, int batch,
+                      const double* dinv, double* B, long long ldb, long long strideb, long long m, double alpha,
+                      void* stream);
+/* rhs [batch, npad, 128] workspace.  Fills z = L^-1 y, alpha = L^-T z (both
+ * [batch, ldv]), quad[b] = |z|^2, logdet[b] = 2 sum log L_ii.                   */
+int plmc_solve_logdet(const double* L, long long ld, long long stride, long long n, long long npad, int batch,
+                      const double* dinv, const double* y, long long ldy, double* rhs, double* z, double* alpha,
+                      long long ldv, double* quad, double* logdet, void* stream);
+/* L -> inv(L) (lower) in place */
+int plmc_trtri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
+                       void* stream);
+/* L -> lower(L^T L) in place */
+int plmc_lauum_batched(double* L, long long ld, long long stride, long long npad, int batch, void* stream);
+/* L -> lower(K^-1) in place = trtri + lauum */
+int plmc_potri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
+                       void* stream);
+
+/* ---- (4) fused backward: autograd of log_prob through the kernel
+ * (experiments.py:270 loss.backward()).  With W = 1/2 (alpha alpha^T - K^-1):
+ *   g_noise[l] = tr W ; g_os[l] = sum W o k ; g_ell[l,k] = d lp / d ell[l,k].
+ * Kinv: lower tiles of K^-1; partial: workspace of plmc_grad_ws(...) bytes.    */
+long long plmc_grad_ws(long long npad, int d, int q);
+int plmc_grad_sweep(const double* Kinv, long long ld, long long stride, const double* alpha, long long lda_vec,
+                    const double* Z, const double* zn, const double* ell, int kernel_id, const double* os,
+                    double* g_ell, double* g_os, double* g_noise, double* partial, long long n, long long npad, int d,
+                    int dpad, int q, void* stream);
+
+/* ---- prediction: eval ProjectedGPModel.__call__, projected_lmc.py:1121-1155 +
+ * gpytorch exact_prediction.  Given V = L^-1 Kx (trsm op 2 applied to Kx):
+ *   lat_mean[l, j] = sum_i alpha[l,i] Kx[l,i,j]  (call before the trsm)
+ *   lat_var [l, j] = os[l]*k(0) - sum_i V[l,i,j]^2                              */
+int plmc_latent_mean(const double* Kx, long long ldx, long long stride, const double* alpha, long long lda_vec,
+                     double* lat_mean, long long ldm, long long n, long long mt, int q, void* stream);
+int plmc_latent_var(const double* V, long long ldx, long long stride, const double* os, double* lat_var,
+                    long long ldm, long long npad, long long mt, int q, void* stream);
+/* mean[j,t] (+)= sum_l lat_mean[l,j] H[l,t]; var[j,t] (+)= sum_l lat_var[l,j] H[l,t]^2
+ * (+ var_add[t] when accumulate == 0).  H [q, p] row-major (= lmc_coefficients()). */
+int plmc_mix_tasks(const double* lat_mean, const double* lat_var, long long ldm, const double* H,
+                   const double* var_add, double* mean, double* var, long long mt, int p, int q, int accumulate,
+                   void* stream);
+
+/* ---- generic FP64 tensor-core GEMM (exposed for tests and roofline runs)
+ * layout bit0: B(k,n) n-contiguous, bit1: A(m,k) m-contiguous (see gemm_dmma.cuh) */
+int plmc_gemm(int layout, const double* A, long long lda, long long sA, const double* B, long long ldb, long long sB,
+              double* C, long long ldc, long long sC, int M, int N, int K, double alpha, double beta, int lower,
+              int triA, int triB, int batch, void* stream);
+
+/* ---- roofline denominators (time with CUDA events on `stream`) */
+int plmc_peak_dmma(int blocks, int threads, long long iters, double* scratch, void* stream);
+int plmc_peak_dfma(int blocks, int threads, long long iters, double* scratch, void* stream);
+int plmc_peak_copy(const double* src, double* dst, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,118 @@
+"""ctypes binding of libplmc_b200.so (the C ABI declared in include/plmc_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a tensor is not a
+CUDA tensor the call raises.  PyTorch is used only for device memory and the
+current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_double, c_int, c_longlong, c_void_p
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "libplmc_b200.so"
+_lib = None
+_inited_devices = set()
+
+P, LL, I, D = c_void_p, c_longlong, c_int, c_double
+
+# name -> argtypes (restype is int unless listed in _RET_LL)
+_SIGNATURES = {
+    "plmc_version": [],
+    "plmc_init": [],
+    "plmc_npad": [LL],
+    "plmc_dinv_bytes": [LL, I],
+    "plmc_project_fwd": [P, P, P, LL, I, I, LL, P],
+    "plmc_project_bwd_ws": [LL, I, I],
+    "plmc_project_bwd": [P, P, LL, P, P, LL, I, I, P],
+    "plmc_col_mean": [P, LL, I, P, P],
+    "plmc_scale_inputs": [P, P, P, P, P, LL, I, I, LL, I, P],
+    "plmc_gram": [P, P, I, P, P, P, LL, LL, LL, LL, I, I, P],
+    "plmc_cross_gram": [P, P, P, P, I, P, P, LL, LL, LL, LL, LL, LL, I, I, P],
+    "plmc_potrf_batched": [P, LL, LL, LL, I, P, P, P],
+    "plmc_trsm_batched": [I, P, LL, LL, LL, I, P, P, LL, LL, LL, D, P],
+    "plmc_solve_logdet": [P, LL, LL, LL, LL, I, P, P, LL, P, P, P, LL, P, P, P],
+    "plmc_trtri_batched": [P, LL, LL, LL, I, P, P],
+    "plmc_lauum_batched": [P, LL, LL, LL, I, P],
+    "plmc_potri_batched": [P, LL, LL, LL, I, P, P],
+    "plmc_grad_ws": [LL, I, I],
+    "plmc_grad_sweep": [P, LL, LL, P, LL, P, P, P, I, P, P, P, P, P, LL, LL, I, I, I, P],
+    "plmc_latent_mean": [P, LL, LL, P, LL, P, LL, LL, LL, I, P],
+    "plmc_latent_var": [P, LL, LL, P, P, LL, LL, LL, I, P],
+    "plmc_mix_tasks": [P, P, LL, P, P, P, P, LL, I, I, I, P],
+    "plmc_gemm": [I, P, LL, LL, P, LL, LL, P, LL, LL, I, I, I, D, D, I, I, I, I, P],
+    "plmc_peak_dmma": [I, I, LL, P, P],
+    "plmc_peak_dfma": [I, I, LL, P, P],
+    "plmc_peak_copy": [P, P, LL, P],
+}
+_RET_LL = {"plmc_npad", "plmc_dinv_bytes", "plmc_project_bwd_ws", "plmc_grad_ws"}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+class PlmcError(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (no device work).  Raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise PlmcError(
+                f"{_LIB_PATH} not found: build it with `python -m projected_lmc_b200.build` "
+                "(there is no CPU fallback for the projected-LMC hot path)"
+            )
+        lib = ctypes.CDLL(str(_LIB_PATH))
+        for name, argtypes in _SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:  # an incomplete build must not be usable
+                raise PlmcError(f"{_LIB_PATH} does not export {name}; rebuild it") from e
+            fn.argtypes = argtypes
+            fn.restype = LL if name in _RET_LL else I
+        _lib = lib
+    return _lib
+
+
+def lib():
+    """Library handle ready for device calls on the current CUDA device."""
+    l = load()
+    if not torch.cuda.is_available():
+        raise PlmcError("projected_lmc_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+    dev = torch.cuda.current_device()
+    if dev not in _inited_devices:
+        rc = l.plmc_init()
+        if rc != 0:
+            raise PlmcError(f"plmc_init failed with {rc} (is this an sm_100a device?)")
+        _inited_devices.add(dev)
+    return l
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise PlmcError(f"libplmc_b200 call {what} failed with code {rc}")
+
+
+def ptr(t) -> c_void_p:
+    if t is None:
+        return c_void_p(0)
+    if not t.is_cuda:
+        raise PlmcError("libplmc_b200 was handed a non-CUDA tensor; there is no CPU fallback")
+    if t.dtype not in (torch.float64, torch.int32):
+        raise PlmcError(f"libplmc_b200 works on float64 / int32 buffers, got {t.dtype}")
+    return c_void_p(t.data_ptr())
+
+
+def stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def npad(n: int) -> int:
+    return ((int(n) + 127) // 128) * 128

@@ -1,0 +1,166 @@
+// C ABI: factorisation layer (see include/plmc_b200.h for the contract).
+#include "linalg.cuh"
+
+using namespace plmc;
+
+namespace plmc {
+
+// rhs[b, i, 0] = y[b, i] (i < n), everything else zero
+__global__ void pack_rhs_kernel(const double* __restrict__ y, long long ldy, double* __restrict__ rhs, long long n,
+                                long long npad) {
+    const int b = blockIdx.z;
+    const long long total = npad * 128;
+    double* R = rhs + (long long)b * total;
+    const double* Y = y + (long long)b * ldy;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long i = idx >> 7;
+        const int c = (int)(idx & 127);
+        R[idx] = (c == 0 && i < n) ? Y[i] : 0.0;
+    }
+}
+
+// out[b, i] = rhs[b, i, 0]
+__global__ void unpack_rhs_kernel(const double* __restrict__ rhs, double* __restrict__ out, long long ldv,
+                                  long long n, long long npad) {
+    const int b = blockIdx.z;
+    const double* R = rhs + (long long)b * npad * 128;
+    double* O = out + (long long)b * ldv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        O[i] = R[i * 128];
+}
+
+// quad[b] = sum z_i^2 ; logdet[b] = 2 sum log L_ii   (fixed-order reduction)
+__global__ void __launch_bounds__(1024) quad_logdet_kernel(const double* __restrict__ z, long long ldv,
+                                                            const double* __restrict__ L, long long ld,
+                                                            long long stride, long long n, double* __restrict__ quad,
+                                                            double* __restrict__ logdet) {
+    __shared__ double sh[32];
+    const int b = blockIdx.x;
+    const double* Z = z + (long long)b * ldv;
+    const double* Lb = L + (long long)b * stride;
+    double sq = 0.0, sl = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) {
+        const double v = Z[i];
+        sq += v * v;
+        sl += log(Lb[i * ld + i]);
+    }
+    sq = block_sum<1024>(sq, sh);
+    sl = block_sum<1024>(sl, sh);
+    if (threadIdx.x == 0) {
+        quad[b] = sq;
+        logdet[b] = 2.0 * sl;
+    }
+}
+
+}  // namespace plmc
+
+extern "C" {
+
+int plmc_version(void) { return 100; }
+
+int plmc_init(void) { return gemm_init_attrs(); }
+
+long long plmc_npad(long long n) { return ((n + 127) / 128) * 128; }
+
+long long plmc_dinv_bytes(long long npad, int batch) { return npad * 128 * 8 * (long long)batch; }
+
+int plmc_gemm(int layout, const double* A, long long lda, long long sA, const double* B, long long ldb, long long sB,
+              double* C, long long ldc, long long sC, int M, int N, int K, double alpha, double beta, int lower,
+              int triA, int triB, int batch, void* stream) {
+    if (!A || !B || !C) return PLMC_ERR_BADARG;
+    GemmArgs g;
+    g.A = A; g.B = B; g.C = C;
+    g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+    g.sA = sA; g.sB = sB; g.sC = sC;
+    g.M = M; g.N = N; g.K = K;
+    g.alpha = alpha; g.beta = beta;
+    g.lower = lower; g.triA = triA; g.triB = triB;
+    const bool aKC = !(layout & 2), bKC = !(layout & 1);
+    return gemm_launch(aKC, bKC, g, batch, (cudaStream_t)stream);
+}
+
+static bool bad_mat(const void* p, long long ld, long long npad, int batch) {
+    return !p || npad <= 0 || (npad % 128) || ld < npad || (ld & 1) || batch <= 0 || batch > 65535 ||
+           npad > 2147483647LL;
+}
+
+int plmc_potrf_batched(double* K, long long ld, long long stride, long long npad, int batch, double* dinv, int* info,
+                       void* stream) {
+    if (bad_mat(K, ld, npad, batch) || !dinv || !info) return PLMC_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(info, 0, sizeof(int) * batch, st) != cudaSuccess) return PLMC_ERR_LAUNCH;
+    LaCtx cx{st, batch, 0};
+    potrf_lower(cx, BMat{K, ld, stride}, (int)npad, DinvBuf{dinv, npad * 128}, 0, info);
+    return cx.status;
+}
+
+int plmc_trsm_batched(int op, const double* L, long long ld, long long stride, long long npad, int batch,
+                      const double* dinv, double* B, long long ldb, long long strideb, long long m, double alpha,
+                      void* stream) {
+    if (bad_mat(L, ld, npad, batch) || !dinv || !B || m <= 0 || (m % 128) || (ldb & 1)) return PLMC_ERR_BADARG;
+    LaCtx cx{(cudaStream_t)stream, batch, 0};
+    BMat Lm{const_cast<double*>(L), ld, stride};
+    DinvBuf D{const_cast<double*>(dinv), npad * 128};
+    BMat Bm{B, ldb, strideb};
+    switch (op) {
+        case 0: trsm_rlt(cx, Lm, (int)npad, D, 0, Bm, (int)m, alpha); break;
+        case 1: trsm_rln(cx, Lm, (int)npad, D, 0, Bm, (int)m, alpha); break;
+        case 2: trsm_lln(cx, Lm, (int)npad, D, 0, Bm, (int)m, alpha); break;
+        case 3: trsm_llt(cx, Lm, (int)npad, D, 0, Bm, (int)m, alpha); break;
+        default: return PLMC_ERR_BADARG;
+    }
+    return cx.status;
+}
+
+int plmc_solve_logdet(const double* L, long long ld, long long stride, long long n, long long npad, int batch,
+                      const double* dinv, const double* y, long long ldy, double* rhs, double* z, double* alpha,
+                      long long ldv, double* quad, double* logdet, void* stream) {
+    if (bad_mat(L, ld, npad, batch) || !dinv || !y || !rhs || !z || !alpha || !quad || !logdet || n <= 0 ||
+        n > npad || ldv < n || ldy < n)
+        return PLMC_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gx = (int)((npad * 128 + 255) / 256 < 1184 ? (npad * 128 + 255) / 256 : 1184);
+    pack_rhs_kernel<<<dim3(gx, 1, batch), 256, 0, st>>>(y, ldy, rhs, n, npad);
+    PLMC_CHECK_LAUNCH();
+    LaCtx cx{st, batch, 0};
+    BMat Lm{const_cast<double*>(L), ld, stride};
+    DinvBuf D{const_cast<double*>(dinv), npad * 128};
+    BMat R{rhs, 128, npad * 128};
+    trsm_lln(cx, Lm, (int)npad, D, 0, R, 128, 1.0);
+    if (cx.status) return cx.status;
+    const int gu = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    unpack_rhs_kernel<<<dim3(gu, 1, batch), 256, 0, st>>>(rhs, z, ldv, n, npad);
+    PLMC_CHECK_LAUNCH();
+    trsm_llt(cx, Lm, (int)npad, D, 0, R, 128, 1.0);
+    if (cx.status) return cx.status;
+    unpack_rhs_kernel<<<dim3(gu, 1, batch), 256, 0, st>>>(rhs, alpha, ldv, n, npad);
+    PLMC_CHECK_LAUNCH();
+    quad_logdet_kernel<<<batch, 1024, 0, st>>>(z, ldv, L, ld, stride, n, quad, logdet);
+    PLMC_CHECK_LAUNCH();
+    return PLMC_OK;
+}
+
+int plmc_trtri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
+                       void* stream) {
+    if (bad_mat(L, ld, npad, batch) || !dinv) return PLMC_ERR_BADARG;
+    LaCtx cx{(cudaStream_t)stream, batch, 0};
+    trtri_lower(cx, BMat{L, ld, stride}, (int)npad, DinvBuf{const_cast<double*>(dinv), npad * 128}, 0);
+    return cx.status;
+}
+
+int plmc_lauum_batched(double* L, long long ld, long long stride, long long npad, int batch, void* stream) {
+    if (bad_mat(L, ld, npad, batch)) return PLMC_ERR_BADARG;
+    LaCtx cx{(cudaStream_t)stream, batch, 0};
+    lauum_lower(cx, BMat{L, ld, stride}, (int)npad);
+    return cx.status;
+}
+
+int plmc_potri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
+                       void* stream) {
+    int r = plmc_trtri_batched(L, ld, stride, npad, batch, dinv, stream);
+    if (r) return r;
+    return plmc_lauum_batched(L, ld, stride, npad, batch, stream);
+}
+}

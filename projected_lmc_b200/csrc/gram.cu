@@ -1,0 +1,476 @@
+// Kernel (2): batched ARD Gram construction (training K + sigma^2 I and the
+// train x test cross block), and kernel (4): the fused backward sweep.
+//
+// Gram semantics follow gpytorch 1.11 as reached from handle_covar_
+// (projected_lmc.py:151-167, evaluated by log_prob at :1201):
+//   x -> (x - mean_rows(x)) / lengthscale,  s_ij = |zi|^2 + |zj|^2 - 2 zi.zj,
+//   clamp_min(0); RBF exp(-s/2); Matern: r = sqrt(max(s, 1e-30)),
+//   nu=5/2: (1 + sqrt5 r + 5/3 r^2) exp(-sqrt5 r); ScaleKernel multiplies by
+//   the outputscale; GaussianLikelihood adds sigma^2 on the diagonal (:1200).
+// The cross term zi.zj runs on the FP64 tensor cores (DMMA.8x8x4), the
+// transform, outputscale, noise/jitter and the identity padding are fused into
+// the epilogue: K is written exactly once (lower 128-tiles only).
+//
+// Algorithmic bytes: 8*q*n(n+1)/2 written (Gram), the same read (sweep).
+#include "plmc_common.cuh"
+
+namespace plmc {
+
+constexpr int GR_THREADS = 256;
+
+__host__ __device__ inline int gram_lds(int dpad) { return ((dpad + 11) / 16) * 16 + 4; }
+
+template <int KID>
+__device__ __forceinline__ double kernel_value(double s) {
+    if (KID == 0) return exp(-0.5 * s);
+    const double r = sqrt(fmax(s, 1e-30));
+    if (KID == 1) {
+        const double a = 2.23606797749978969641 * r;  // sqrt(5) r
+        return (1.0 + a + (5.0 / 3.0) * r * r) * exp(-a);
+    }
+    if (KID == 2) {
+        const double a = 1.73205080756887729353 * r;
+        return (1.0 + a) * exp(-a);
+    }
+    return exp(-r);
+}
+
+// k(s) and dk/ds
+template <int KID>
+__device__ __forceinline__ void kernel_value_grad(double s, double& k, double& dk) {
+    if (KID == 0) {
+        k = exp(-0.5 * s);
+        dk = -0.5 * k;
+        return;
+    }
+    const double r = sqrt(fmax(s, 1e-30));
+    if (KID == 1) {
+        const double a = 2.23606797749978969641 * r;
+        const double e = exp(-a);
+        k = (1.0 + a + (5.0 / 3.0) * r * r) * e;
+        dk = -(5.0 / 6.0) * (1.0 + a) * e;
+    } else if (KID == 2) {
+        const double a = 1.73205080756887729353 * r;
+        const double e = exp(-a);
+        k = (1.0 + a) * e;
+        dk = -1.5 * e;
+    } else {
+        k = exp(-r);
+        dk = (s > 1e-30) ? -0.5 * k / r : 0.0;
+    }
+}
+
+// xmean[k] = mean_i X[i, k]
+__global__ void __launch_bounds__(256) col_mean_kernel(const double* __restrict__ X, long long n, int d,
+                                                       double* __restrict__ xmean) {
+    __shared__ double sh[32];
+    const int k = blockIdx.x;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 256) s += X[i * d + k];
+    s = block_sum<256>(s, sh);
+    if (threadIdx.x == 0) xmean[k] = s / (double)n;
+}
+
+__global__ void __launch_bounds__(256) scale_inputs_kernel(const double* __restrict__ X,
+                                                           const double* __restrict__ xmean,
+                                                           const double* __restrict__ ell, double* __restrict__ Z,
+                                                           double* __restrict__ zn, long long n, int d, int dpad,
+                                                           long long rows_pad) {
+    const int l = blockIdx.z;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows_pad) return;
+    double* z = Z + ((long long)l * rows_pad + i) * dpad;
+    double s = 0.0;
+    for (int k = 0; k < dpad; ++k) {
+        double v = 0.0;
+        if (i < n && k < d) v = (X[i * d + k] - xmean[k]) / ell[(long long)l * d + k];
+        z[k] = v;
+        s = fma(v, v, s);
+    }
+    zn[(long long)l * rows_pad + i] = s;
+}
+
+// MODE 0: training Gram (lower tiles, diagonal noise, identity padding)
+// MODE 1: cross Gram (all tiles; rows >= n are zero)
+template <int KID, int MODE>
+__global__ void __launch_bounds__(GR_THREADS, 1)
+    gram_kernel(const double* __restrict__ Zr, const double* __restrict__ znr, long long rows_pad_r,
+                const double* __restrict__ Zc, const double* __restrict__ znc, long long rows_pad_c,
+                const double* __restrict__ os, const double* __restrict__ diag_add, double* __restrict__ Kout,
+                long long ld, long long stride, long long n, int dpad, int tiles_c) {
+    extern __shared__ __align__(16) double sm[];
+    const int lds = gram_lds(dpad);
+    double* Zi = sm;
+    double* Zj = sm + 128 * lds;
+    double* ni = Zj + 128 * lds;
+    double* nj = ni + 128;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int l = blockIdx.z;
+
+    int ti, tj;
+    if (MODE == 0) {
+        const long long b = blockIdx.x;
+        int r = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+        while ((long long)(r + 1) * (r + 2) / 2 <= b) ++r;
+        while ((long long)r * (r + 1) / 2 > b) --r;
+        ti = r;
+        tj = (int)(b - (long long)r * (r + 1) / 2);
+    } else {
+        ti = blockIdx.x / tiles_c;
+        tj = blockIdx.x - ti * tiles_c;
+    }
+    const long long i0 = (long long)ti * 128, j0 = (long long)tj * 128;
+
+    const double* zr = Zr + ((long long)l * rows_pad_r + i0) * dpad;
+    const double* zc = Zc + ((long long)l * rows_pad_c + j0) * dpad;
+    for (int idx = tid; idx < 128 * dpad; idx += GR_THREADS) {
+        const int r = idx / dpad, k = idx - r * dpad;
+        Zi[r * lds + k] = zr[idx];
+        Zj[r * lds + k] = zc[idx];
+    }
+    if (tid < 128) {
+        ni[tid] = znr[(long long)l * rows_pad_r + i0 + tid];
+        nj[tid] = znc[(long long)l * rows_pad_c + j0 + tid];
+    }
+    __syncthreads();
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const double* pa = Zi + (wm * 64 + g) * lds + t;
+    const double* pb = Zj + (wn * 32 + g) * lds + t;
+    for (int k0 = 0; k0 < dpad; k0 += 4) {
+        double af[8], bf[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) af[i] = pa[i * 8 * lds + k0];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = pb[j * 8 * lds + k0];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+
+    const double osl = os ? os[l] : 1.0;
+    const double dadd = (MODE == 0) ? diag_add[l] : 0.0;
+    double* Kl = Kout + (long long)l * stride;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rl = wm * 64 + i * 8 + g;
+        const long long gi = i0 + rl;
+        const double nri = ni[rl];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int cl = wn * 32 + j * 8 + 2 * t;
+            const long long gj = j0 + cl;
+            double v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long long gje = gj + e;
+                double s = nri + nj[cl + e] - 2.0 * acc[i][j][e];
+                s = fmax(s, 0.0);
+                if (MODE == 0) {
+                    if (gi == gje) s = 0.0;
+                    double kv = osl * kernel_value<KID>(s);
+                    if (gi == gje) kv += dadd;
+                    if (gi >= n || gje >= n) kv = (gi == gje) ? 1.0 : 0.0;
+                    v[e] = kv;
+                } else {
+                    v[e] = (gi < n) ? osl * kernel_value<KID>(s) : 0.0;
+                }
+            }
+            *reinterpret_cast<double2*>(Kl + gi * ld + gj) = make_double2(v[0], v[1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Fused backward sweep.  With W = 1/2 (alpha alpha^T - K^-1) and the symmetric
+// weights w_ij (2 below the diagonal, 1 on it), one pass over the lower tiles of
+// K^-1 accumulates, per latent:
+//   acc[k]      = sum w_ij W_ij os dk/ds (z_ik - z_jk)^2      k < d
+//   acc[dpad]   = sum w_ij W_ij k(s_ij)                        (d lp / d os)
+//   acc[dpad+1] = sum_i W_ii                                   (d lp / d sigma^2)
+// K tiles are recomputed from Z (direct differences); dK is never materialised.
+// partial layout: [q, gridDim.x, dpad + 2]; the reduction is fixed-order.
+// ---------------------------------------------------------------------------
+template <int KID>
+__global__ void __launch_bounds__(GR_THREADS, 1)
+    grad_sweep_kernel(const double* __restrict__ Kinv, long long ld, long long stride,
+                      const double* __restrict__ alpha, long long lda_vec, const double* __restrict__ Z,
+                      const double* __restrict__ os, double* __restrict__ partial, long long n, long long npad,
+                      int dpad, long long ntiles) {
+    extern __shared__ __align__(16) double sm[];
+    const int lds = dpad + 1;
+    double* Zi = sm;                    // [128][lds]
+    double* Zj = Zi + 128 * lds;        // [128][lds]
+    double* ai = Zj + 128 * lds;        // [128]
+    double* aj = ai + 128;              // [128]
+    double* wsum = aj + 128;            // [8][dpad+2]
+    double* cta_acc = wsum + 8 * (dpad + 2);  // [dpad+2]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int l = blockIdx.z;
+    const int nacc = dpad + 2;
+    const double osl = os ? os[l] : 1.0;
+    const double* Kl = Kinv + (long long)l * stride;
+    const double* al = alpha + (long long)l * lda_vec;
+    const double* Zl = Z + (long long)l * npad * dpad;
+
+    if (tid < nacc) cta_acc[tid] = 0.0;
+
+    for (long long b = blockIdx.x; b < ntiles; b += gridDim.x) {
+        int r = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+        while ((long long)(r + 1) * (r + 2) / 2 <= b) ++r;
+        while ((long long)r * (r + 1) / 2 > b) --r;
+        const int ti = r, tj = (int)(b - (long long)r * (r + 1) / 2);
+        const long long i0 = (long long)ti * 128, j0 = (long long)tj * 128;
+
+        __syncthreads();
+        for (int idx = tid; idx < 128 * dpad; idx += GR_THREADS) {
+            const int rr = idx / dpad, k = idx - rr * dpad;
+            Zi[rr * lds + k] = Zl[i0 * dpad + idx];
+            Zj[rr * lds + k] = Zl[j0 * dpad + idx];
+        }
+        if (tid < 128) {
+            ai[tid] = (i0 + tid < n) ? al[i0 + tid] : 0.0;
+            aj[tid] = (j0 + tid < n) ? al[j0 + tid] : 0.0;
+        }
+        __syncthreads();
+
+        // thread patch: rows wm*64 + 8*i + g (i<8), cols wn*32 + 8*j + 2t + e (j<4, e<2)
+        double Wv[8][8];  // first s_ij, then A_ij = w * W * os * dk/ds
+        const int rbase = wm * 64 + g, cbase = wn * 32 + 2 * t;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) Wv[i][c] = 0.0;
+        // squared scaled distances by direct differences
+        for (int k = 0; k < dpad; ++k) {
+            double zi[8], zj[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) zi[i] = Zi[(rbase + i * 8) * lds + k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                zj[2 * j] = Zj[(cbase + j * 8) * lds + k];
+                zj[2 * j + 1] = Zj[(cbase + j * 8 + 1) * lds + k];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const double dlt = zi[i] - zj[c];
+                    Wv[i][c] = fma(dlt, dlt, Wv[i][c]);
+                }
+        }
+        double s_os = 0.0, s_tr = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const long long gi = i0 + rbase + i * 8;
+            const double a_i = ai[rbase + i * 8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int cl0 = cbase + j * 8;
+                const double2 kv = *reinterpret_cast<const double2*>(Kl + gi * ld + j0 + cl0);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = 2 * j + e;
+                    const int cl = cl0 + e;
+                    const long long gj = j0 + cl;
+                    double w = (gj < gi) ? 2.0 : (gj == gi ? 1.0 : 0.0);
+                    if (gi >= n || gj >= n) w = 0.0;
+                    const double Wij = 0.5 * (a_i * aj[cl] - (e ? kv.y : kv.x));
+                    double kk, dk;
+                    kernel_value_grad<KID>(Wv[i][c], kk, dk);
+                    s_os = fma(w * Wij, kk, s_os);
+                    if (gj == gi && gi < n) s_tr += Wij;
+                    Wv[i][c] = w * Wij * osl * dk;
+                }
+            }
+        }
+        // per-dimension accumulation  sum A_ij (z_ik - z_jk)^2
+        for (int k = 0; k < dpad; ++k) {
+            double zi[8], zj[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) zi[i] = Zi[(rbase + i * 8) * lds + k];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                zj[2 * j] = Zj[(cbase + j * 8) * lds + k];
+                zj[2 * j + 1] = Zj[(cbase + j * 8 + 1) * lds + k];
+            }
+            double sk = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const double dlt = zi[i] - zj[c];
+                    sk = fma(Wv[i][c], dlt * dlt, sk);
+                }
+            sk = warp_sum(sk);
+            if (lane == 0) wsum[warp * nacc + k] = sk;
+        }
+        s_os = warp_sum(s_os);
+        s_tr = warp_sum(s_tr);
+        if (lane == 0) {
+            wsum[warp * nacc + dpad] = s_os;
+            wsum[warp * nacc + dpad + 1] = s_tr;
+        }
+        __syncthreads();
+        if (tid < nacc) {
+            double s = 0.0;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) s += wsum[w8 * nacc + tid];
+            cta_acc[tid] += s;
+        }
+    }
+    __syncthreads();
+    if (tid < nacc) partial[((long long)l * gridDim.x + blockIdx.x) * nacc + tid] = cta_acc[tid];
+}
+
+// g_ell[l,k] = -(2/ell[l,k]) * sum_c partial[l,c,k] ; g_os, g_noise likewise
+__global__ void grad_reduce_kernel(const double* __restrict__ partial, int chunks, int d, int dpad,
+                                   const double* __restrict__ ell, double* __restrict__ g_ell,
+                                   double* __restrict__ g_os, double* __restrict__ g_noise) {
+    const int l = blockIdx.x;
+    const int nacc = dpad + 2;
+    for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
+        double s = 0.0;
+        for (int c = 0; c < chunks; ++c) s += partial[((long long)l * chunks + c) * nacc + a];
+        if (a < d)
+            g_ell[(long long)l * d + a] = -2.0 * s / ell[(long long)l * d + a];
+        else if (a == dpad) {
+            if (g_os) g_os[l] = s;
+        } else if (a == dpad + 1)
+            g_noise[l] = s;
+    }
+}
+
+static inline int sweep_ctas(long long ntiles) { return (int)(ntiles < 592 ? ntiles : 592); }
+
+}  // namespace plmc
+
+using namespace plmc;
+
+template <int MODE>
+static int launch_gram(int kernel_id, dim3 grid, size_t smem, cudaStream_t st, const double* Zr, const double* znr,
+                       long long rpr, const double* Zc, const double* znc, long long rpc, const double* os,
+                       const double* diag_add, double* K, long long ld, long long stride, long long n, int dpad,
+                       int tiles_c) {
+#define PLMC_GRAM_CASE(KID)                                                                                     \
+    case KID:                                                                                                   \
+        if (smem > 48 * 1024)                                                                                   \
+            cudaFuncSetAttribute(gram_kernel<KID, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        gram_kernel<KID, MODE><<<grid, GR_THREADS, smem, st>>>(Zr, znr, rpr, Zc, znc, rpc, os, diag_add, K, ld,  \
+                                                               stride, n, dpad, tiles_c);                       \
+        break;
+    switch (kernel_id) {
+        PLMC_GRAM_CASE(0)
+        PLMC_GRAM_CASE(1)
+        PLMC_GRAM_CASE(2)
+        PLMC_GRAM_CASE(3)
+        default: return PLMC_ERR_BADARG;
+    }
+#undef PLMC_GRAM_CASE
+    PLMC_CHECK_LAUNCH();
+    return PLMC_OK;
+}
+
+extern "C" {
+
+int plmc_col_mean(const double* X, long long n, int d, double* xmean, void* stream) {
+    if (!X || !xmean || n <= 0 || d <= 0) return PLMC_ERR_BADARG;
+    col_mean_kernel<<<d, 256, 0, (cudaStream_t)stream>>>(X, n, d, xmean);
+    PLMC_CHECK_LAUNCH();
+    return PLMC_OK;
+}
+
+int plmc_scale_inputs(const double* X, const double* xmean, const double* ell, double* Z, double* zn, long long n,
+                      int d, int dpad, long long rows_pad, int q, void* stream) {
+    if (!X || !xmean || !ell || !Z || !zn || n <= 0 || d <= 0 || dpad < d || (dpad & 3) || rows_pad < n || q <= 0)
+        return PLMC_ERR_BADARG;
+    dim3 grid((unsigned)((rows_pad + 255) / 256), 1, q);
+    scale_inputs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, xmean, ell, Z, zn, n, d, dpad, rows_pad);
+    PLMC_CHECK_LAUNCH();
+    return PLMC_OK;
+}
+
+int plmc_gram(const double* Z, const double* zn, int kernel_id, const double* os, const double* diag_add, double* K,
+              long long ld, long long stride, long long n, long long npad, int dpad, int q, void* stream) {
+    if (!Z || !zn || !diag_add || !K || n <= 0 || npad < n || (npad % 128) || ld < npad || (ld & 1) || dpad <= 0 ||
+        (dpad & 3) || q <= 0 || q > 65535)
+        return PLMC_ERR_BADARG;
+    const long long tm = npad / 128;
+    const long long tiles = tm * (tm + 1) / 2;
+    if (tiles > 2147483647LL) return PLMC_ERR_BADARG;
+    const size_t smem = (size_t)(2 * 128 * gram_lds(dpad) + 256) * 8;
+    if (smem > 227 * 1024) return PLMC_ERR_BADARG;
+    return launch_gram<0>(kernel_id, dim3((unsigned)tiles, 1, q), smem, (cudaStream_t)stream, Z, zn, npad, Z, zn, npad,
+                          os, diag_add, K, ld, stride, n, dpad, (int)tm);
+}
+
+int plmc_cross_gram(const double* Ztrain, const double* zntrain, const double* Ztest, const double* zntest,
+                    int kernel_id, const double* os, double* Kx, long long ldx, long long stride, long long n,
+                    long long npad, long long mt_rows_pad, long long mt, int dpad, int q, void* stream) {
+    if (!Ztrain || !zntrain || !Ztest || !zntest || !Kx || n <= 0 || npad < n || (npad % 128) || mt <= 0 ||
+        (mt % 128) || mt_rows_pad < mt || ldx < mt || (ldx & 1) || dpad <= 0 || (dpad & 3) || q <= 0 || q > 65535)
+        return PLMC_ERR_BADARG;
+    const long long tr = npad / 128, tc = mt / 128;
+    if (tr * tc > 2147483647LL) return PLMC_ERR_BADARG;
+    const size_t smem = (size_t)(2 * 128 * gram_lds(dpad) + 256) * 8;
+    if (smem > 227 * 1024) return PLMC_ERR_BADARG;
+    return launch_gram<1>(kernel_id, dim3((unsigned)(tr * tc), 1, q), smem, (cudaStream_t)stream, Ztrain, zntrain,
+                          npad, Ztest, zntest, mt_rows_pad, os, nullptr, Kx, ldx, stride, n, dpad, (int)tc);
+}
+
+long long plmc_grad_ws(long long npad, int d, int q) {
+    if (npad <= 0 || d <= 0 || q <= 0) return 0;
+    const long long tm = npad / 128;
+    const int dpad = ((d + 3) / 4) * 4;
+    return (long long)q * sweep_ctas(tm * (tm + 1) / 2) * (dpad + 2) * 8;
+}
+
+int plmc_grad_sweep(const double* Kinv, long long ld, long long stride, const double* alpha, long long lda_vec,
+                    const double* Z, const double* zn, const double* ell, int kernel_id, const double* os,
+                    double* g_ell, double* g_os, double* g_noise, double* partial, long long n, long long npad, int d,
+                    int dpad, int q, void* stream) {
+    (void)zn;
+    if (!Kinv || !alpha || !Z || !ell || !g_ell || !g_noise || !partial || n <= 0 || npad < n || (npad % 128) ||
+        ld < npad || (ld & 1) || d <= 0 || dpad < d || (dpad & 3) || dpad != ((d + 3) / 4) * 4 || q <= 0 ||
+        q > 65535 || lda_vec < n)
+        return PLMC_ERR_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long tm = npad / 128;
+    const long long ntiles = tm * (tm + 1) / 2;
+    const int ctas = sweep_ctas(ntiles);
+    const size_t smem = (size_t)(2 * 128 * (dpad + 1) + 256 + 9 * (dpad + 2)) * 8;
+    if (smem > 227 * 1024) return PLMC_ERR_BADARG;
+    dim3 grid(ctas, 1, q);
+#define PLMC_SWEEP_CASE(KID)                                                                                     \
+    case KID:                                                                                                    \
+        if (smem > 48 * 1024)                                                                                    \
+            cudaFuncSetAttribute(grad_sweep_kernel<KID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        grad_sweep_kernel<KID><<<grid, GR_THREADS, smem, st>>>(Kinv, ld, stride, alpha, lda_vec, Z, os, partial, n, \
+                                                               npad, dpad, ntiles);                              \
+        break;
+    switch (kernel_id) {
+        PLMC_SWEEP_CASE(0)
+        PLMC_SWEEP_CASE(1)
+        PLMC_SWEEP_CASE(2)
+        PLMC_SWEEP_CASE(3)
+        default: return PLMC_ERR_BADARG;
+    }
+#undef PLMC_SWEEP_CASE
+    PLMC_CHECK_LAUNCH();
+    grad_reduce_kernel<<<q, 64, 0, st>>>(partial, ctas, d, dpad, ell, g_ell, g_os, g_noise);
+    PLMC_CHECK_LAUNCH();
+    return PLMC_OK;
+}
+}

@@ -1,0 +1,268 @@
+#include "linalg.cuh"
+
+namespace plmc {
+
+// ---------------------------------------------------------------------------
+// 128x128 Cholesky leaf, one CTA per batch member, matrix resident in shared
+// memory.  Replaces the inner potrf of torch.linalg.cholesky_ex that
+// gpytorch's psd_safe_cholesky calls (reached from projected_lmc.py:1201).
+// Also writes inv(L_leaf) to Dinv so TRSM leaves become GEMMs.
+// ---------------------------------------------------------------------------
+constexpr int LEAF = 128;
+constexpr int LEAF_LD = 129;
+constexpr int LEAF_THREADS = 256;
+constexpr int LEAF_SMEM = (LEAF * LEAF_LD + LEAF) * 8;
+
+__global__ void __launch_bounds__(LEAF_THREADS, 1)
+    potrf_leaf_kernel(double* __restrict__ Abase, long long ld, long long sA, double* __restrict__ Dbase,
+                      long long sD, int* __restrict__ info, int row_off) {
+    extern __shared__ __align__(16) double S[];
+    double* xd = S + LEAF * LEAF_LD;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    double* A = Abase + (long long)b * sA;
+    double* D = Dbase + (long long)b * sD;
+
+    for (int idx = tid; idx < LEAF * LEAF; idx += LEAF_THREADS) {
+        const int r = idx >> 7, c = idx & 127;
+        if (c <= r) S[r * LEAF_LD + c] = A[(long long)r * ld + c];
+    }
+
+    // right-looking, unscaled columns (scaling deferred): one barrier per column
+    const int tx = tid & 15, ty = tid >> 4;
+    int fail = 0;
+    for (int j = 0; j < LEAF; ++j) {
+        __syncthreads();
+        const double d = S[j * LEAF_LD + j];
+        if (!(d > 0.0)) {
+            fail = j + 1;
+            break;
+        }
+        const double rd = 1.0 / d;
+        for (int i = j + 1 + ty; i < LEAF; i += 16) {
+            const double lij = S[i * LEAF_LD + j] * rd;
+            for (int k = j + 1 + tx; k <= i; k += 16) S[i * LEAF_LD + k] -= lij * S[k * LEAF_LD + j];
+        }
+    }
+    __syncthreads();
+    if (fail && tid == 0 && info[b] == 0) info[b] = row_off + fail;
+    // scale columns: L[i][j] = S[i][j] / sqrt(S[j][j])
+    for (int idx = tid; idx < LEAF * LEAF; idx += LEAF_THREADS) {
+        const int r = idx >> 7, c = idx & 127;
+        if (c < r) S[r * LEAF_LD + c] *= rsqrt(S[c * LEAF_LD + c]);
+    }
+    __syncthreads();
+    if (tid < LEAF) S[tid * LEAF_LD + tid] = sqrt(S[tid * LEAF_LD + tid]);
+    __syncthreads();
+
+    // write back L (lower part only)
+    for (int idx = tid; idx < LEAF * LEAF; idx += LEAF_THREADS) {
+        const int r = idx >> 7, c = idx & 127;
+        if (c <= r) A[(long long)r * ld + c] = S[r * LEAF_LD + c];
+    }
+
+    // inverse by forward substitution, 2 threads per column; column j of
+    // X = inv(L) is kept transposed in row j of the (free) upper triangle.
+    {
+        const int j = tid >> 1, h = tid & 1;
+        const int kmin = (tid >> 5) * 16;  // smallest column owned by this warp
+        if (h == 0) xd[j] = 1.0 / S[j * LEAF_LD + j];
+        __syncwarp();
+        for (int i = kmin + 1; i < LEAF; ++i) {
+            double s = 0.0;
+            for (int k = kmin + h; k < i; k += 2) {
+                if (k >= j) {
+                    const double xk = (k == j) ? xd[j] : S[j * LEAF_LD + k];
+                    s += S[i * LEAF_LD + k] * xk;
+                }
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            if (h == 0 && j < i) S[j * LEAF_LD + i] = -s / S[i * LEAF_LD + i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < LEAF * LEAF; idx += LEAF_THREADS) {
+        const int r = idx >> 7, c = idx & 127;
+        double v = 0.0;
+        if (c < r)
+            v = S[c * LEAF_LD + r];
+        else if (c == r)
+            v = xd[r];
+        D[r * LEAF + c] = v;
+    }
+}
+
+// copy Dinv leaves over the diagonal blocks (lower part) : final step of trtri
+__global__ void dinv_to_diag_kernel(double* __restrict__ Lbase, long long ld, long long sL,
+                                    const double* __restrict__ Dbase, long long sD) {
+    const int blk = blockIdx.x, b = blockIdx.z;
+    double* L = Lbase + (long long)b * sL + (long long)blk * LEAF * ld + (long long)blk * LEAF;
+    const double* D = Dbase + (long long)b * sD + (long long)blk * LEAF * LEAF;
+    for (int idx = threadIdx.x; idx < LEAF * LEAF; idx += blockDim.x) {
+        const int r = idx >> 7, c = idx & 127;
+        if (c <= r) L[(long long)r * ld + c] = D[idx];
+    }
+}
+
+static bool g_leaf_attr_done = false;
+static int leaf_attr() {
+    if (!g_leaf_attr_done) {
+        if (cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM) !=
+            cudaSuccess)
+            return PLMC_ERR_LAUNCH;
+        g_leaf_attr_done = true;
+    }
+    return PLMC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host-side helpers
+// ---------------------------------------------------------------------------
+static inline int split128(int n) { return ((n / LEAF) / 2) * LEAF; }
+
+static void gemm(LaCtx& cx, bool aKC, bool bKC, BMat A, BMat B, BMat C, int M, int N, int K, double alpha,
+                 double beta, int lower = 0, int triA = 0, int triB = 0) {
+    if (cx.status) return;
+    GemmArgs g;
+    g.A = A.p; g.B = B.p; g.C = C.p;
+    g.lda = A.ld; g.ldb = B.ld; g.ldc = C.ld;
+    g.sA = A.stride; g.sB = B.stride; g.sC = C.stride;
+    g.M = M; g.N = N; g.K = K;
+    g.alpha = alpha; g.beta = beta;
+    g.lower = lower; g.triA = triA; g.triB = triB;
+    cx.status = gemm_launch(aKC, bKC, g, cx.batch, cx.st);
+}
+
+void potrf_lower(LaCtx& cx, BMat A, int n, DinvBuf D, long long blk0, int* info) {
+    if (cx.status || n <= 0) return;
+    if (n == LEAF) {
+        if ((cx.status = leaf_attr())) return;
+        BMat d = D.leaf(blk0);
+        potrf_leaf_kernel<<<cx.batch, LEAF_THREADS, LEAF_SMEM, cx.st>>>(A.p, A.ld, A.stride, d.p, d.stride, info,
+                                                                        (int)(blk0 * LEAF));
+        if (cudaGetLastError() != cudaSuccess) cx.status = PLMC_ERR_LAUNCH;
+        return;
+    }
+    const int n1 = split128(n), n2 = n - n1;
+    BMat A11 = A, A21 = A.sub(n1, 0), A22 = A.sub(n1, n1);
+    potrf_lower(cx, A11, n1, D, blk0, info);
+    trsm_rlt(cx, A11, n1, D, blk0, A21, n2, 1.0);
+    // A22 -= A21 * A21^T   (lower tiles only)
+    gemm(cx, true, true, A21, A21, A22, n2, n2, n1, -1.0, 1.0, /*lower=*/1);
+    potrf_lower(cx, A22, n2, D, blk0 + n1 / LEAF, info);
+}
+
+// X L^T = alpha B ;  L^T = [[L11^T, L21^T],[0, L22^T]]
+void trsm_rlt(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha) {
+    if (cx.status || n <= 0 || m <= 0) return;
+    if (n == LEAF) {  // X = alpha * B * Dinv^T
+        gemm(cx, true, true, B, D.leaf(blk0), B, m, LEAF, LEAF, alpha, 0.0);
+        return;
+    }
+    const int n1 = split128(n), n2 = n - n1;
+    BMat B1 = B, B2 = B.sub(0, n1);
+    trsm_rlt(cx, L, n1, D, blk0, B1, m, alpha);
+    // B2 = alpha*B2 - X1 * L21^T
+    gemm(cx, true, true, B1, L.sub(n1, 0), B2, m, n2, n1, -1.0, alpha);
+    trsm_rlt(cx, L.sub(n1, n1), n2, D, blk0 + n1 / LEAF, B2, m, 1.0);
+}
+
+// X L = alpha B ;  X2 first
+void trsm_rln(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha) {
+    if (cx.status || n <= 0 || m <= 0) return;
+    if (n == LEAF) {  // X = alpha * B * Dinv
+        gemm(cx, true, false, B, D.leaf(blk0), B, m, LEAF, LEAF, alpha, 0.0);
+        return;
+    }
+    const int n1 = split128(n), n2 = n - n1;
+    BMat B1 = B, B2 = B.sub(0, n1);
+    trsm_rln(cx, L.sub(n1, n1), n2, D, blk0 + n1 / LEAF, B2, m, alpha);
+    // B1 = alpha*B1 - X2 * L21
+    gemm(cx, true, false, B2, L.sub(n1, 0), B1, m, n1, n2, -1.0, alpha);
+    trsm_rln(cx, L, n1, D, blk0, B1, m, 1.0);
+}
+
+// L X = alpha B
+void trsm_lln(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha) {
+    if (cx.status || n <= 0 || m <= 0) return;
+    if (n == LEAF) {  // X = alpha * Dinv * B
+        gemm(cx, true, false, D.leaf(blk0), B, B, LEAF, m, LEAF, alpha, 0.0);
+        return;
+    }
+    const int n1 = split128(n), n2 = n - n1;
+    BMat B1 = B, B2 = B.sub(n1, 0);
+    trsm_lln(cx, L, n1, D, blk0, B1, m, alpha);
+    // B2 = alpha*B2 - L21 * X1
+    gemm(cx, true, false, L.sub(n1, 0), B1, B2, n2, m, n1, -1.0, alpha);
+    trsm_lln(cx, L.sub(n1, n1), n2, D, blk0 + n1 / LEAF, B2, m, 1.0);
+}
+
+// L^T X = alpha B ;  X2 first
+void trsm_llt(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha) {
+    if (cx.status || n <= 0 || m <= 0) return;
+    if (n == LEAF) {  // X = alpha * Dinv^T * B
+        gemm(cx, false, false, D.leaf(blk0), B, B, LEAF, m, LEAF, alpha, 0.0);
+        return;
+    }
+    const int n1 = split128(n), n2 = n - n1;
+    BMat B1 = B, B2 = B.sub(n1, 0);
+    trsm_llt(cx, L.sub(n1, n1), n2, D, blk0 + n1 / LEAF, B2, m, alpha);
+    // B1 = alpha*B1 - L21^T * X2
+    gemm(cx, false, false, L.sub(n1, 0), B2, B1, n1, m, n2, -1.0, alpha);
+    trsm_llt(cx, L, n1, D, blk0, B1, m, 1.0);
+}
+
+static void trtri_rec(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
+    if (cx.status || n <= LEAF) return;
+    const int n1 = split128(n), n2 = n - n1;
+    BMat L21 = L.sub(n1, 0), L22 = L.sub(n1, n1);
+    // L21 := -inv(L22) * L21 * inv(L11), using the not-yet-inverted L11, L22
+    trsm_rln(cx, L, n1, D, blk0, L21, n2, 1.0);
+    trsm_lln(cx, L22, n2, D, blk0 + n1 / LEAF, L21, n1, -1.0);
+    trtri_rec(cx, L, n1, D, blk0);
+    trtri_rec(cx, L22, n2, D, blk0 + n1 / LEAF);
+}
+
+void trtri_lower(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
+    if (cx.status || n <= 0) return;
+    trtri_rec(cx, L, n, D, blk0);
+    if (cx.status) return;
+    dim3 grid(n / LEAF, 1, cx.batch);
+    BMat d0 = D.leaf(blk0);
+    dinv_to_diag_kernel<<<grid, 256, 0, cx.st>>>(L.p, L.ld, L.stride, d0.p, d0.stride);
+    if (cudaGetLastError() != cudaSuccess) cx.status = PLMC_ERR_LAUNCH;
+}
+
+// B := T^T B
+void trmm_llt(LaCtx& cx, BMat T, int n, BMat B, int m) {
+    if (cx.status || n <= 0 || m <= 0) return;
+    if (n == LEAF) {
+        gemm(cx, false, false, T, B, B, LEAF, m, LEAF, 1.0, 0.0, 0, /*triA=*/1, 0);
+        return;
+    }
+    const int n1 = split128(n), n2 = n - n1;
+    BMat B1 = B, B2 = B.sub(n1, 0);
+    trmm_llt(cx, T, n1, B1, m);
+    // B1 += T21^T * B2
+    gemm(cx, false, false, T.sub(n1, 0), B2, B1, n1, m, n2, 1.0, 1.0);
+    trmm_llt(cx, T.sub(n1, n1), n2, B2, m);
+}
+
+void lauum_lower(LaCtx& cx, BMat L, int n) {
+    if (cx.status || n <= 0) return;
+    if (n == LEAF) {  // C = T^T T (full symmetric tile written)
+        gemm(cx, false, false, L, L, L, LEAF, LEAF, LEAF, 1.0, 0.0, 0, 1, 1);
+        return;
+    }
+    const int n1 = split128(n), n2 = n - n1;
+    BMat L21 = L.sub(n1, 0), L22 = L.sub(n1, n1);
+    lauum_lower(cx, L, n1);
+    // L11 += L21^T L21  (lower tiles)
+    gemm(cx, false, false, L21, L21, L, n1, n1, n2, 1.0, 1.0, /*lower=*/1);
+    // L21 := L22^T L21
+    trmm_llt(cx, L22, n2, L21, n1);
+    lauum_lower(cx, L22, n2);
+}
+
+}  // namespace plmc

@@ -1,0 +1,53 @@
+// Batched blocked dense linear algebra on top of the DMMA GEMM.
+//
+// Every routine is a recursive (cache-oblivious) block algorithm whose leaves
+// are 128x128: all O(n^3) work is done by gemm_dmma_kernel; the only other
+// compute kernel on the factorisation path is the 128x128 shared-memory
+// Cholesky leaf, which also emits the explicit inverse of its factor (Dinv) so
+// that every triangular-solve leaf is again a GEMM.
+//
+// All matrices: row-major, order n % 128 == 0, batch via stride.
+#pragma once
+#include "gemm_dmma.cuh"
+
+namespace plmc {
+
+struct BMat {  // batched matrix view
+    double* p;
+    long long ld;
+    long long stride;
+    __host__ BMat sub(long long r, long long c) const { return BMat{p + r * ld + c, ld, stride}; }
+};
+
+struct LaCtx {
+    cudaStream_t st;
+    int batch;
+    int status;  // first non-zero launch status
+};
+
+// Dinv: per batch member, n/128 consecutive 128x128 row-major blocks holding
+// inv(L_kk) (upper part explicitly zero).  stride = (n/128)*16384.
+struct DinvBuf {
+    double* p;
+    long long stride;
+    __host__ BMat leaf(long long blk) const { return BMat{p + blk * 16384, 128, stride}; }
+};
+
+// A (lower) -> L in place; info[b] = 0 or 1-based index of first non-positive pivot.
+void potrf_lower(LaCtx& cx, BMat A, int n, DinvBuf D, long long blk0, int* info);
+// X * L^T = alpha*B    (B: m x n, in place)
+void trsm_rlt(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha);
+// X * L = alpha*B
+void trsm_rln(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha);
+// L * X = alpha*B      (B: n x m, in place)
+void trsm_lln(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha);
+// L^T * X = alpha*B
+void trsm_llt(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha);
+// L -> inv(L) in place (needs Dinv from potrf_lower)
+void trtri_lower(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0);
+// L -> lower(L^T L) in place
+void lauum_lower(LaCtx& cx, BMat L, int n);
+// B := T^T * B  (T lower n x n, B n x m)
+void trmm_llt(LaCtx& cx, BMat T, int n, BMat B, int m);
+
+}  // namespace plmc

@@ -1,0 +1,165 @@
+// Kernel (1): the Y -> latent projection  TY = T^T Y^T  and its adjoint.
+//
+// Replaces ProjectedGPModel.project_data (projected_lmc.py:1014-1021), whose
+// two matmuls + triangular solve are algebraically TY = T^T Y^T with
+// T = projection_matrix() (:1003-1012).  T is tiny and is formed on the host
+// (autograd keeps dT -> dH, dM, dnoise there); this file is the HBM-bound part:
+// one streaming pass over Y [n, p].
+//
+// Algorithmic bytes: 8*n*(p+q) forward, the same backward.
+#include "plmc_common.cuh"
+
+namespace plmc {
+
+constexpr int PJ_ROWS = 64;   // rows of Y per tile
+constexpr int PJ_PC = 32;     // task chunk
+constexpr int PJ_QC = 32;     // latent chunk (gridDim.y)
+constexpr int PJ_THREADS = 256;
+
+// TY[l, i] = sum_t T[t, l] * Y[i, t]
+__global__ void __launch_bounds__(PJ_THREADS) project_fwd_kernel(const double* __restrict__ Y,
+                                                                 const double* __restrict__ T,
+                                                                 double* __restrict__ TY, long long n, int p, int q,
+                                                                 long long ldty) {
+    __shared__ double Ys[PJ_ROWS][PJ_PC + 1];
+    __shared__ double Ts[PJ_PC][PJ_QC];
+    const int tid = threadIdx.x;
+    const long long r0 = (long long)blockIdx.x * PJ_ROWS;
+    const int q0 = blockIdx.y * PJ_QC;
+    const int qc = min(PJ_QC, q - q0);
+    const int row = tid & 63, lg = tid >> 6;
+    double acc[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) acc[a] = 0.0;
+
+    for (int p0 = 0; p0 < p; p0 += PJ_PC) {
+        const int pc = min(PJ_PC, p - p0);
+        __syncthreads();
+        for (int idx = tid; idx < PJ_ROWS * pc; idx += PJ_THREADS) {
+            const int r = idx / pc, c = idx - r * pc;
+            const long long gr = r0 + r;
+            Ys[r][c] = (gr < n) ? Y[gr * p + p0 + c] : 0.0;
+        }
+        for (int idx = tid; idx < PJ_PC * PJ_QC; idx += PJ_THREADS) {
+            const int t = idx >> 5, l = idx & 31;
+            Ts[t][l] = (t < pc && l < qc) ? T[(long long)(p0 + t) * q + q0 + l] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int t = 0; t < pc; ++t) {
+            const double y = Ys[row][t];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) acc[a] = fma(y, Ts[t][lg + 4 * a], acc[a]);
+        }
+    }
+    const long long gr = r0 + row;
+    if (gr < n) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int l = lg + 4 * a;
+            if (l < qc) TY[(long long)(q0 + l) * ldty + gr] = acc[a];
+        }
+    }
+}
+
+// partial[c, t, l] = sum_{i in chunk c} Y[i, t] * G[l, i]
+__global__ void __launch_bounds__(PJ_THREADS) project_bwd_kernel(const double* __restrict__ Y,
+                                                                 const double* __restrict__ G, long long ldg,
+                                                                 double* __restrict__ partial, long long n, int p,
+                                                                 int q, long long rows_per_cta) {
+    __shared__ double Ys[PJ_ROWS][PJ_PC + 1];
+    __shared__ double Gs[PJ_QC][PJ_ROWS + 1];
+    const int tid = threadIdx.x;
+    const long long rbeg = (long long)blockIdx.x * rows_per_cta;
+    const long long rend = min(n, rbeg + rows_per_cta);
+    const int q0 = blockIdx.y * PJ_QC;
+    const int qc = min(PJ_QC, q - q0);
+    const int tt = tid & 31, lg = tid >> 5;
+    double* out = partial + (long long)blockIdx.x * p * q;
+
+    for (int p0 = 0; p0 < p; p0 += PJ_PC) {
+        const int pc = min(PJ_PC, p - p0);
+        double acc[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[a] = 0.0;
+        for (long long r0 = rbeg; r0 < rend; r0 += PJ_ROWS) {
+            __syncthreads();
+            for (int idx = tid; idx < PJ_ROWS * pc; idx += PJ_THREADS) {
+                const int r = idx / pc, c = idx - r * pc;
+                const long long gr = r0 + r;
+                Ys[r][c] = (gr < rend) ? Y[gr * p + p0 + c] : 0.0;
+            }
+            for (int idx = tid; idx < PJ_QC * PJ_ROWS; idx += PJ_THREADS) {
+                const int l = idx >> 6, r = idx & 63;
+                const long long gr = r0 + r;
+                Gs[l][r] = (gr < rend && l < qc) ? G[(long long)(q0 + l) * ldg + gr] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int r = 0; r < PJ_ROWS; ++r) {
+                const double y = Ys[r][tt];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) acc[a] = fma(y, Gs[lg + 8 * a][r], acc[a]);
+            }
+        }
+        if (tt < pc) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int l = lg + 8 * a;
+                if (l < qc) out[(long long)(p0 + tt) * q + q0 + l] = acc[a];
+            }
+        }
+    }
+}
+
+// dT[e] = sum_c partial[c, e]   (fixed order -> deterministic)
+__global__ void reduce_chunks_kernel(const double* __restrict__ partial, double* __restrict__ out, long long elems,
+                                     int chunks) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= elems) return;
+    double s = 0.0;
+    for (int c = 0; c < chunks; ++c) s += partial[(long long)c * elems + e];
+    out[e] = s;
+}
+
+static inline int bwd_chunks(long long n) {
+    long long c = (n + PJ_ROWS - 1) / PJ_ROWS;
+    return (int)(c < 296 ? c : 296);
+}
+
+}  // namespace plmc
+
+using namespace plmc;
+
+extern "C" {
+
+int plmc_project_fwd(const double* Y, const double* T, double* TY, long long n, int p, int q, long long ldty,
+                     void* stream) {
+    if (!Y || !T || !TY || n <= 0 || p <= 0 || q <= 0 || ldty < n) return PLMC_ERR_BADARG;
+    dim3 grid((unsigned)((n + PJ_ROWS - 1) / PJ_ROWS), (q + PJ_QC - 1) / PJ_QC);
+    project_fwd_kernel<<<grid, PJ_THREADS, 0, (cudaStream_t)stream>>>(Y, T, TY, n, p, q, ldty);
+    PLMC_CHECK_LAUNCH();
+    return PLMC_OK;
+}
+
+long long plmc_project_bwd_ws(long long n, int p, int q) {
+    if (n <= 0 || p <= 0 || q <= 0) return 0;
+    return (long long)bwd_chunks(n) * p * q * 8;
+}
+
+int plmc_project_bwd(const double* Y, const double* G, long long ldg, double* dT, double* partial, long long n, int p,
+                     int q, void* stream) {
+    if (!Y || !G || !dT || !partial || n <= 0 || p <= 0 || q <= 0 || ldg < n) return PLMC_ERR_BADARG;
+    const int chunks = bwd_chunks(n);
+    long long rows = (n + chunks - 1) / chunks;
+    rows = ((rows + PJ_ROWS - 1) / PJ_ROWS) * PJ_ROWS;
+    const int used = (int)((n + rows - 1) / rows);
+    dim3 grid(used, (q + PJ_QC - 1) / PJ_QC);
+    project_bwd_kernel<<<grid, PJ_THREADS, 0, (cudaStream_t)stream>>>(Y, G, ldg, partial, n, p, q, rows);
+    PLMC_CHECK_LAUNCH();
+    const long long elems = (long long)p * q;
+    reduce_chunks_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, dT, elems, used);
+    PLMC_CHECK_LAUNCH();
+    return PLMC_OK;
+}
+}
