@@ -1,0 +1,157 @@
+"""GPU parity: the CUDA path (through the model API and the C ABI) against the CPU oracle.
+
+Tolerances (north_star, fp64): MLL 1e-8 relative, gradients / predictive means / variances
+1e-6 relative.  The tests assert a tighter 1e-9 / 1e-7 so regressions show early."""
+import warnings
+
+import pytest
+import torch
+
+from oracle import plmc_oracle as O
+from projected_lmc_b200 import ProjectedLMCmll, gp
+
+from .helpers import VARIANTS, cpu_copy, make_model, oracle_params, rel_err, synth
+
+pytestmark = pytest.mark.gpu
+
+MLL_TOL = 1e-9
+GRAD_TOL = 1e-7
+PRED_TOL = 1e-7
+
+
+def run_case(n, d, p, q, variant, kernel, outputscales=False, ns=37, seed=0):
+    X, Y, Xs, _ = synth(n, d, p, q, seed=seed, ns=ns)
+    m = make_model(X, Y, q, variant=variant, kernel=kernel, outputscales=outputscales, seed=seed)
+    mc = cpu_copy(m)
+    m = m.cuda()
+    Xg, Yg = X.cuda(), Y.cuda()
+    m.train()
+    mll = ProjectedLMCmll(m.likelihood, m)
+    loss = -mll(m(Xg), Yg)
+    loss.backward()
+
+    mc.train()
+    op = oracle_params(mc)
+    ref = -O.mll(op, X, Y)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= MLL_TOL * abs(ref.item()), (loss.item(), ref.item())
+    ref_grads = dict(mc.named_parameters())
+    for name, prm in m.named_parameters():
+        g_ref = ref_grads[name].grad
+        if g_ref is None:
+            assert prm.grad is None or prm.grad.abs().max().item() == 0.0, name
+            continue
+        assert prm.grad is not None, name
+        assert rel_err(prm.grad, g_ref) <= GRAD_TOL, (name, prm.grad.cpu(), g_ref)
+
+    # prediction
+    m.eval()
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fl = m.full_likelihood()
+        lat = m(Xs.cuda())
+        obs = fl(lat)
+        mean_ref, varf_ref, vary_ref = O.predict(oracle_params(mc), X, Y, Xs)
+    assert rel_err(lat.mean, mean_ref) <= PRED_TOL
+    assert rel_err(lat.variance, varf_ref) <= PRED_TOL
+    assert rel_err(obs.variance, vary_ref) <= PRED_TOL
+    lo, hi = obs.confidence_region()
+    assert torch.allclose(hi - lo, 4 * obs.stddev)
+    return m
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("kernel", ["rbf", "matern52"])
+def test_variants_small(variant, kernel):
+    run_case(n=150, d=3, p=7, q=3, variant=variant, kernel=kernel)
+
+
+@pytest.mark.parametrize("kernel", ["matern32", "matern12"])
+def test_other_matern(kernel):
+    run_case(n=90, d=2, p=5, q=2, variant="PLMC", kernel=kernel)
+
+
+def test_outputscales():
+    m = run_case(n=140, d=4, p=6, q=2, variant="PLMC", kernel="matern52", outputscales=True)
+    assert m.outputscale().shape == (2, 1)
+
+
+def test_ragged_sizes():
+    # n not a multiple of the 128 tile, n < 128, d not a multiple of 4, q = 1, d = 1
+    run_case(n=33, d=1, p=4, q=1, variant="PLMC_fast", kernel="matern52", ns=5)
+    run_case(n=129, d=5, p=9, q=4, variant="PLMC", kernel="rbf", ns=130)
+    run_case(n=384, d=6, p=12, q=5, variant="BDN_diag", kernel="rbf", ns=257)
+
+
+def test_config1_shape():
+    # BASELINE config 1: n=1000, d=6, 50 tasks, 10 latents, RBF, fp64
+    run_case(n=1000, d=6, p=50, q=10, variant="PLMC", kernel="rbf", ns=200)
+    run_case(n=1000, d=6, p=50, q=10, variant="PLMC_fast", kernel="rbf", ns=64)
+
+
+def test_sarcos_shape_reduced():
+    # config 2 shape (d=21, 7 tasks, 4 latents, Matern-5/2 ARD) at an oracle-sized n
+    run_case(n=1500, d=21, p=7, q=4, variant="PLMC", kernel="matern52", ns=100)
+
+
+def test_api_helpers():
+    X, Y, _, _ = synth(100, 3, 6, 2)
+    m = make_model(X, Y, 2, variant="PLMC", kernel="rbf").cuda()
+    assert m.lscales().shape == (2, 3)
+    with pytest.raises(AttributeError):
+        m.outputscale()
+    assert m.projection_matrix().shape == (6, 2)
+    TY = m.project_data(Y.cuda())
+    assert TY.shape == (2, 100)
+    T = m.projection_matrix()
+    assert rel_err(TY, (Y.cuda() @ T).T) < 1e-12
+    assert m.projected_noise().shape == (2,)
+    assert m.B_tilde().shape == (4, 4)
+    assert m.lmc_coefficients().shape == (2, 6)
+    with pytest.raises(RuntimeError):
+        m(X.cuda()[:50])  # must train on the training inputs
+
+
+def test_cpu_tensors_fail_loudly():
+    from projected_lmc_b200._cabi import PlmcError
+
+    X, Y, _, _ = synth(64, 2, 4, 2)
+    m = make_model(X, Y, 2)
+    mll = ProjectedLMCmll(m.likelihood, m)
+    with pytest.raises(PlmcError):
+        mll(m(X), Y)
+
+
+def test_jitter_retry_matches_oracle():
+    # duplicate points + tiny noise -> first factorisation fails, jitter is added to the failing latent only
+    X, Y, _, _ = synth(120, 2, 5, 2)
+    X[60:] = X[:60]
+    m = make_model(X, Y, 2, variant="PLMC_fast", kernel="rbf", perturb=False, noise_thresh=-40.0)
+    with torch.no_grad():
+        m.likelihood.noise_covar.raw_noise[0] = -60.0
+    mc = cpu_copy(m)
+    m = m.cuda()
+    mll = ProjectedLMCmll(m.likelihood, m)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        with gp.settings.cholesky_max_tries(8):
+            val = mll(m(X.cuda()), Y.cuda()).item()
+        ref = O.mll(oracle_params(mc), X, Y, max_tries=8).item()
+    assert m._engine.last_jitter is not None and m._engine.last_jitter[1].item() == 0.0
+    assert abs(val - ref) <= 1e-6 * abs(ref)
+
+
+def test_loo_matches_dense():
+    X, Y, _, _ = synth(130, 3, 5, 2)
+    m = make_model(X, Y, 2, variant="PLMC", kernel="matern52")
+    mc = cpu_copy(m)
+    m = m.cuda()
+    s2, r = m.compute_loo()
+    op = oracle_params(mc)
+    with torch.no_grad():
+        K = O.gram(op, X, training=False) + torch.diag_embed(O.noise(op)[:, None].expand(-1, 130))
+        Kinv = torch.linalg.inv(K)
+        TY = O.project_data(op, Y)
+        s2_ref = 1.0 / torch.diagonal(Kinv, dim1=1, dim2=2)
+        r_ref = (Kinv @ TY.unsqueeze(-1)).squeeze(-1) * s2_ref
+    assert rel_err(s2, s2_ref.T) < 1e-8 and rel_err(r, r_ref.T) < 1e-8
