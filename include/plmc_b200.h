@@ -16,7 +16,8 @@
  *   - return value: 0 ok, -1 bad argument, -2 launch failure.  Numerical
  *     failure (non-PD matrix) is reported LAPACK-style in a device `info`
  *     array, never through the return code;
- *   - re-entrant, no global mutable state beyond one-time function attributes;
+ *   - re-entrant; the only global state is one-time function attributes and the
+ *     atomic launch counters behind plmc_stats_*;
  *   - FP64 throughout; matrices row-major; "npad" = n rounded up to 128.
  */
 #ifndef PLMC_B200_H
@@ -34,6 +35,11 @@ extern "C" {
 int plmc_version(void);
 /* one-time per device: opt in to >48 KB dynamic shared memory for the kernels */
 int plmc_init(void);
+/* host-side launch statistics since the last reset: kernels launched by this
+ * library, GEMM launches among them, and their algorithmic FLOPs (2*M*N*K over the
+ * tiles actually computed).  Outputs are HOST pointers (may be NULL).            */
+int plmc_stats_reset(void);
+int plmc_stats_get(long long* launches_host, long long* gemm_launches_host, double* gemm_flops_host);
 /* npad for a problem of order n (multiple of 128) */
 long long plmc_npad(long long n);
 /* bytes of the Dinv side buffer potrf needs for `batch` matrices of order npad */

@@ -22,6 +22,8 @@ P, LL, I, D = c_void_p, c_longlong, c_int, c_double
 _SIGNATURES = {
     "plmc_version": [],
     "plmc_init": [],
+    "plmc_stats_reset": [],
+    "plmc_stats_get": [P, P, P],
     "plmc_npad": [LL],
     "plmc_dinv_bytes": [LL, I],
     "plmc_project_fwd": [P, P, P, LL, I, I, LL, P],

@@ -62,6 +62,16 @@ int plmc_version(void) { return 100; }
 
 int plmc_init(void) { return gemm_init_attrs(); }
 
+int plmc_stats_reset(void) {
+    stats_reset();
+    return PLMC_OK;
+}
+
+int plmc_stats_get(long long* launches_host, long long* gemm_launches_host, double* gemm_flops_host) {
+    stats_get(launches_host, gemm_launches_host, gemm_flops_host);
+    return PLMC_OK;
+}
+
 long long plmc_npad(long long n) { return ((n + 127) / 128) * 128; }
 
 long long plmc_dinv_bytes(long long npad, int batch) { return npad * 128 * 8 * (long long)batch; }
@@ -139,6 +149,7 @@ int plmc_solve_logdet(const double* L, long long ld, long long stride, long long
     PLMC_CHECK_LAUNCH();
     quad_logdet_kernel<<<batch, 1024, 0, st>>>(z, ldv, L, ld, stride, n, quad, logdet);
     PLMC_CHECK_LAUNCH();
+    note_launch(4);
     return PLMC_OK;
 }
 

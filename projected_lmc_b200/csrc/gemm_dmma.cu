@@ -1,6 +1,32 @@
 #include "gemm_dmma.cuh"
 
+#include <atomic>
+
 namespace plmc {
+
+static std::atomic<long long> g_launches{0};
+static std::atomic<long long> g_gemm_launches{0};
+static std::atomic<double> g_gemm_flops{0.0};
+
+void note_launch(long long kernels, double gemm_flops) {
+    g_launches.fetch_add(kernels, std::memory_order_relaxed);
+    if (gemm_flops > 0.0) {
+        g_gemm_launches.fetch_add(1, std::memory_order_relaxed);
+        double cur = g_gemm_flops.load(std::memory_order_relaxed);
+        while (!g_gemm_flops.compare_exchange_weak(cur, cur + gemm_flops, std::memory_order_relaxed)) {
+        }
+    }
+}
+void stats_get(long long* launches, long long* gemm_launches, double* gemm_flops) {
+    if (launches) *launches = g_launches.load();
+    if (gemm_launches) *gemm_launches = g_gemm_launches.load();
+    if (gemm_flops) *gemm_flops = g_gemm_flops.load();
+}
+void stats_reset() {
+    g_launches = 0;
+    g_gemm_launches = 0;
+    g_gemm_flops = 0.0;
+}
 
 int gemm_init_attrs() {
     cudaError_t e;
@@ -38,6 +64,7 @@ int gemm_launch(bool aKC, bool bKC, const GemmArgs& a, int batch, cudaStream_t s
     else
         gemm_dmma_kernel<false, false><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
     PLMC_CHECK_LAUNCH();
+    note_launch(1, 2.0 * (double)tiles * G_BM * G_BN * (double)a.K * batch);
     return PLMC_OK;
 }
 

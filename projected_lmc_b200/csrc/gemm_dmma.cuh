@@ -193,6 +193,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(const GemmArgs 
 enum GemmLayout { A_KC_B_KC = 0, A_KC_B_NC = 1, A_MC_B_KC = 2, A_MC_B_NC = 3 };
 
 int gemm_init_attrs();
+void stats_get(long long* launches, long long* gemm_launches, double* gemm_flops);
+void stats_reset();
 // op layouts: aKC -> A(m,k) at A[m*lda+k] else A[k*lda+m];  bKC -> B(k,n) at B[n*ldb+k] else B[k*ldb+n]
 int gemm_launch(bool aKC, bool bKC, const GemmArgs& a, int batch, cudaStream_t st);
 

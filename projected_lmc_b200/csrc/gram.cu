@@ -380,6 +380,7 @@ static int launch_gram(int kernel_id, dim3 grid, size_t smem, cudaStream_t st, c
     }
 #undef PLMC_GRAM_CASE
     PLMC_CHECK_LAUNCH();
+    note_launch(1);
     return PLMC_OK;
 }
 
@@ -389,6 +390,7 @@ int plmc_col_mean(const double* X, long long n, int d, double* xmean, void* stre
     if (!X || !xmean || n <= 0 || d <= 0) return PLMC_ERR_BADARG;
     col_mean_kernel<<<d, 256, 0, (cudaStream_t)stream>>>(X, n, d, xmean);
     PLMC_CHECK_LAUNCH();
+    note_launch(1);
     return PLMC_OK;
 }
 
@@ -399,6 +401,7 @@ int plmc_scale_inputs(const double* X, const double* xmean, const double* ell, d
     dim3 grid((unsigned)((rows_pad + 255) / 256), 1, q);
     scale_inputs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, xmean, ell, Z, zn, n, d, dpad, rows_pad);
     PLMC_CHECK_LAUNCH();
+    note_launch(1);
     return PLMC_OK;
 }
 
@@ -469,8 +472,10 @@ int plmc_grad_sweep(const double* Kinv, long long ld, long long stride, const do
     }
 #undef PLMC_SWEEP_CASE
     PLMC_CHECK_LAUNCH();
+    note_launch(1);
     grad_reduce_kernel<<<q, 64, 0, st>>>(partial, ctas, d, dpad, ell, g_ell, g_os, g_noise);
     PLMC_CHECK_LAUNCH();
+    note_launch(1);
     return PLMC_OK;
 }
 }

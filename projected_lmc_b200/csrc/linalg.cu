@@ -142,6 +142,7 @@ void potrf_lower(LaCtx& cx, BMat A, int n, DinvBuf D, long long blk0, int* info)
         potrf_leaf_kernel<<<cx.batch, LEAF_THREADS, LEAF_SMEM, cx.st>>>(A.p, A.ld, A.stride, d.p, d.stride, info,
                                                                         (int)(blk0 * LEAF));
         if (cudaGetLastError() != cudaSuccess) cx.status = PLMC_ERR_LAUNCH;
+        note_launch(1);
         return;
     }
     const int n1 = split128(n), n2 = n - n1;
@@ -232,6 +233,7 @@ void trtri_lower(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
     BMat d0 = D.leaf(blk0);
     dinv_to_diag_kernel<<<grid, 256, 0, cx.st>>>(L.p, L.ld, L.stride, d0.p, d0.stride);
     if (cudaGetLastError() != cudaSuccess) cx.status = PLMC_ERR_LAUNCH;
+    note_launch(1);
 }
 
 // B := T^T B

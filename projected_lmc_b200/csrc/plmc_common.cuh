@@ -26,6 +26,9 @@
 
 namespace plmc {
 
+// host-side launch statistics (read through plmc_stats_get; bench.py reports them)
+void note_launch(long long kernels, double gemm_flops = 0.0);
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
     uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes));

@@ -139,6 +139,7 @@ int plmc_latent_mean(const double* Kx, long long ldx, long long stride, const do
     col_reduce_kernel<false><<<grid, 1024, 0, (cudaStream_t)stream>>>(Kx, ldx, stride, alpha, lda_vec, nullptr,
                                                                       lat_mean, ldm, n, mt);
     PLMC_CHECK_LAUNCH();
+    note_launch(1);
     return PLMC_OK;
 }
 
@@ -150,6 +151,7 @@ int plmc_latent_var(const double* V, long long ldx, long long stride, const doub
     col_reduce_kernel<true><<<grid, 1024, 0, (cudaStream_t)stream>>>(V, ldx, stride, nullptr, 0, os, lat_var, ldm,
                                                                      npad, mt);
     PLMC_CHECK_LAUNCH();
+    note_launch(1);
     return PLMC_OK;
 }
 
@@ -162,6 +164,7 @@ int plmc_mix_tasks(const double* lat_mean, const double* lat_var, long long ldm,
     mix_tasks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(lat_mean, lat_var, ldm, H, var_add, mean, var, mt, p, q,
                                                              accumulate);
     PLMC_CHECK_LAUNCH();
+    note_launch(1);
     return PLMC_OK;
 }
 }

@@ -139,6 +139,7 @@ int plmc_project_fwd(const double* Y, const double* T, double* TY, long long n, 
     dim3 grid((unsigned)((n + PJ_ROWS - 1) / PJ_ROWS), (q + PJ_QC - 1) / PJ_QC);
     project_fwd_kernel<<<grid, PJ_THREADS, 0, (cudaStream_t)stream>>>(Y, T, TY, n, p, q, ldty);
     PLMC_CHECK_LAUNCH();
+    note_launch(1);
     return PLMC_OK;
 }
 
@@ -157,9 +158,11 @@ int plmc_project_bwd(const double* Y, const double* G, long long ldg, double* dT
     dim3 grid(used, (q + PJ_QC - 1) / PJ_QC);
     project_bwd_kernel<<<grid, PJ_THREADS, 0, (cudaStream_t)stream>>>(Y, G, ldg, partial, n, p, q, rows);
     PLMC_CHECK_LAUNCH();
+    note_launch(1);
     const long long elems = (long long)p * q;
     reduce_chunks_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, dT, elems, used);
     PLMC_CHECK_LAUNCH();
+    note_launch(1);
     return PLMC_OK;
 }
 }

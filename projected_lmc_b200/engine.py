@@ -68,7 +68,9 @@ class LatentEngine:
         K, dinv, info = ws["K"], ws["dinv"], ws["info"]
         jitter = torch.zeros(q, dtype=torch.float64, device=Z.device)
         ops.gram(Z, zn, kid, os_, noise, K, n)
+        self._mark("gram")
         ops.potrf(K, dinv, info)
+        self._mark("potrf")
         bad = info.cpu()
         if not bool(bad.any()):
             self.last_jitter = None
@@ -100,16 +102,41 @@ class LatentEngine:
         q = ell.shape[0]
         ws = self.workspace(X.device, q, n)
         np_ = ws["K"].shape[1]
+        mark = self._mark
+        mark("start")
         Z, zn = ops.scale_inputs(X, self.xmean(X), ell, np_)
         self._gram_potrf(ws, Z, zn, kid, os_, noise, n, max_tries)
+        mark("retry")
         K, dinv = ws["K"], ws["dinv"]
         z, alpha, quad, logdet = ops.solve_logdet(K, dinv, TY, n, ws["rhs"])
         lp = -0.5 * (quad + logdet + n * math.log(2 * math.pi))
+        mark("solve_logdet")
         if not need_grad:
             return lp, None
         ops.potri(K, dinv)
+        mark("potri")
         g_ell, g_os, g_noise = ops.grad_sweep(K, alpha, Z, zn, ell, kid, os_, n)
+        mark("grad_sweep")
         return lp, (-alpha, g_ell, (g_os if os_ is not None else None), g_noise)
+
+    # -- optional phase timing (CUDA events on the launch stream; used by bench.py) --
+    profile = None
+
+    def _mark(self, name):
+        if self.profile is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.profile.append((name, ev))
+
+    def phase_ms(self):
+        """Sum of the recorded phase durations (ms) by name; call after a synchronize."""
+        out = {}
+        prev = None
+        for name, ev in self.profile or []:
+            if name != "start" and prev is not None:
+                out[name] = out.get(name, 0.0) + prev.elapsed_time(ev)
+            prev = ev
+        return out
 
     # -- leave-one-out by-product (projected_lmc.py:1108-1119) ----------------------
     def loo(self, X, TY, ell, os_, noise, kid, max_tries=None):

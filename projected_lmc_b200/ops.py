@@ -202,3 +202,16 @@ def peak_copy(src, dst):
     n = src.numel()
     check(lib().plmc_peak_copy(ptr(src), ptr(dst), n, stream()), "peak_copy")
     return 16 * n
+
+
+def stats_reset():
+    check(_cabi.load().plmc_stats_reset(), "stats_reset")
+
+
+def stats_get():
+    """(kernel launches, GEMM launches, GEMM algorithmic FLOPs) since the last reset."""
+    import ctypes
+
+    a, b, c = ctypes.c_longlong(0), ctypes.c_longlong(0), ctypes.c_double(0.0)
+    check(_cabi.load().plmc_stats_get(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "stats_get")
+    return a.value, b.value, c.value
