@@ -28,17 +28,37 @@ void stats_reset() {
     g_gemm_flops = 0.0;
 }
 
+template <bool A, bool B, bool T>
+static int set_attr() {
+    return cudaFuncSetAttribute(gemm_dmma_kernel<A, B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                G_SMEM_BYTES) == cudaSuccess
+               ? PLMC_OK
+               : PLMC_ERR_LAUNCH;
+}
+
 int gemm_init_attrs() {
-    cudaError_t e;
-    e = cudaFuncSetAttribute(gemm_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
-    if (e != cudaSuccess) return PLMC_ERR_LAUNCH;
-    e = cudaFuncSetAttribute(gemm_dmma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
-    if (e != cudaSuccess) return PLMC_ERR_LAUNCH;
-    e = cudaFuncSetAttribute(gemm_dmma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
-    if (e != cudaSuccess) return PLMC_ERR_LAUNCH;
-    e = cudaFuncSetAttribute(gemm_dmma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM_BYTES);
-    if (e != cudaSuccess) return PLMC_ERR_LAUNCH;
-    return PLMC_OK;
+    int r = 0;
+    r |= set_attr<true, true, false>();
+    r |= set_attr<true, false, false>();
+    r |= set_attr<false, true, false>();
+    r |= set_attr<false, false, false>();
+    r |= set_attr<true, true, true>();
+    r |= set_attr<true, false, true>();
+    r |= set_attr<false, true, true>();
+    r |= set_attr<false, false, true>();
+    return r ? PLMC_ERR_LAUNCH : PLMC_OK;
+}
+
+template <bool T>
+static void launch_variant(bool aKC, bool bKC, dim3 grid, cudaStream_t st, const GemmArgs& a) {
+    if (aKC && bKC)
+        gemm_dmma_kernel<true, true, T><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
+    else if (aKC && !bKC)
+        gemm_dmma_kernel<true, false, T><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
+    else if (!aKC && bKC)
+        gemm_dmma_kernel<false, true, T><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
+    else
+        gemm_dmma_kernel<false, false, T><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
 }
 
 int gemm_launch(bool aKC, bool bKC, const GemmArgs& a, int batch, cudaStream_t st) {
@@ -55,14 +75,10 @@ int gemm_launch(bool aKC, bool bKC, const GemmArgs& a, int batch, cudaStream_t s
     }
     if (tiles > 2147483647LL || batch > 65535) return PLMC_ERR_BADARG;
     dim3 grid((unsigned)tiles, 1, (unsigned)batch);
-    if (aKC && bKC)
-        gemm_dmma_kernel<true, true><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
-    else if (aKC && !bKC)
-        gemm_dmma_kernel<true, false><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
-    else if (!aKC && bKC)
-        gemm_dmma_kernel<false, true><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
+    if (a.triA || a.triB)
+        launch_variant<true>(aKC, bKC, grid, st, a);
     else
-        gemm_dmma_kernel<false, false><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
+        launch_variant<false>(aKC, bKC, grid, st, a);
     PLMC_CHECK_LAUNCH();
     note_launch(1, 2.0 * (double)tiles * G_BM * G_BN * (double)a.K * batch);
     return PLMC_OK;

@@ -7,28 +7,41 @@
 // projected_lmc.py:1201).
 //
 // Shape contract (guaranteed by the padding the Gram builder applies):
-//   M % 128 == 0, N % 128 == 0, K % 16 == 0, all leading dims % 2 == 0,
+//   M % 128 == 0, N % 128 == 0, K % G_BK == 0, all leading dims % 2 == 0,
 //   all base pointers 16-byte aligned.  No bounds checks in the hot loop.
 //
-// CTA tile 128x128x16, 8 warps (2 x 4), warp tile 64x32 -> 32 DMMA per k4 step
+// CTA tile 128x128xG_BK, 8 warps (2 x 4), warp tile 64x32 -> 32 DMMA per k4 step
 // per warp against 12 LDS.64: the kernel is DMMA-issue bound by construction.
-// Operands are staged with 16-byte cp.async into a 4-stage shared-memory ring.
+// Operands are staged with 16-byte cp.async into a shared-memory ring; all
+// per-thread global/shared addresses are loop invariant (one 64-bit add per chunk
+// per k-tile) and the two warps that share an SM sub-partition issue their copies
+// at different points of the k-tile so the tensor pipe always has a warp feeding it.
 // Shared layouts are padded so that every fragment load is bank-conflict free:
-//   k-contiguous operand  -> tile[128][16+4]
-//   m/n-contiguous operand-> tile[16][128+4]
+//   k-contiguous operand  -> tile[128][G_BK+4]
+//   m/n-contiguous operand-> tile[G_BK][128+4]
 #pragma once
 #include "plmc_common.cuh"
 
 namespace plmc {
 
-constexpr int G_BM = 128, G_BN = 128, G_BK = 16;
+#ifndef PLMC_GEMM_BK
+#define PLMC_GEMM_BK 32
+#endif
+#ifndef PLMC_GEMM_STAGES
+#define PLMC_GEMM_STAGES 3
+#endif
+
+constexpr int G_BM = 128, G_BN = 128, G_BK = PLMC_GEMM_BK;
 constexpr int G_THREADS = 256;
-constexpr int G_STAGES = 4;
-constexpr int G_LDK = G_BK + 4;    // 20
-constexpr int G_LDM = G_BM + 4;    // 132
-constexpr int G_TILE = 128 * G_LDK;  // 2560 doubles >= 16*132
+constexpr int G_STAGES = PLMC_GEMM_STAGES;
+constexpr int G_LDK = G_BK + 4;      // k-contiguous tile row stride (doubles); (G_BK+4) % 16 == 4
+constexpr int G_LDM = G_BM + 4;      // m-contiguous tile row stride
+constexpr int G_TILE = (128 * G_LDK > G_BK * G_LDM) ? 128 * G_LDK : G_BK * G_LDM;
 constexpr int G_STAGE = 2 * G_TILE;  // A + B
-constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE * 8;  // 163840
+constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE * 8;
+constexpr int G_NCH = G_BK / 4;      // 16-byte chunks per thread per operand per k-tile
+static_assert(G_BK % 16 == 0 && (G_LDK % 16) == 4, "fragment loads must stay conflict free");
+static_assert(G_SMEM_BYTES <= 227 * 1024, "shared memory ring too large");
 
 struct GemmArgs {
     const double* A;
@@ -43,43 +56,66 @@ struct GemmArgs {
     int triB;
 };
 
-// Load one 128 x 16 operand tile.  KC: element (x, k) at P[(x0+x)*ld + k0+k].
-// MC: element (x, k) at P[(k0+k)*ld + x0+x].  `tri` masks stored col > stored row.
-template <bool KC>
-__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ P, long long ld, int x0, int k0,
-                                          int tri, int tid) {
-    if (KC) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = tid + i * G_THREADS;
-            const int row = c >> 3, ch = c & 7;
-            const int gr = x0 + row, gc = k0 + ch * 2;
-            int bytes = 16;
-            if (tri) {
-                int v = gr - gc + 1;
-                v = v < 0 ? 0 : (v > 2 ? 2 : v);
-                bytes = v * 8;
-            }
-            cp_async16(s + row * G_LDK + ch * 2, P + (long long)gr * ld + gc, bytes);
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = tid + i * G_THREADS;
-            const int krow = c >> 6, ch = c & 63;
-            const int gr = k0 + krow, gc = x0 + ch * 2;
-            int bytes = 16;
-            if (tri) {
-                int v = gr - gc + 1;
-                v = v < 0 ? 0 : (v > 2 ? 2 : v);
-                bytes = v * 8;
-            }
-            cp_async16(s + krow * G_LDM + ch * 2, P + (long long)gr * ld + gc, bytes);
-        }
-    }
+__device__ __forceinline__ void cp_async16s(uint32_t smem_addr, const void* gmem_src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr), "l"(gmem_src), "r"(src_bytes));
 }
 
-template <bool A_KC, bool B_KC>
+// Per-thread copy plan for one operand: G_NCH chunks per k-tile.
+//   KC: element (x, k) at P[(x0+x)*ld + k],  chunk c -> row c / (G_BK/2), col-pair c % (G_BK/2)
+//   MC: element (x, k) at P[k*ld + x0+x],    chunk c -> k-row c / 64,     col-pair c % 64
+template <bool KC, bool TRI>
+struct TileLoader {
+    const double* g0;   // running global pointer of chunk 0 (advances by one k-tile per load)
+    long long step;     // elements between consecutive chunks of this thread
+    long long adv;      // elements per k-tile
+    uint32_t soff;      // byte offset of chunk 0 inside a tile
+    int r0, c0;         // stored (row, col) of chunk 0 at k-tile 0 (TRI only)
+    bool mask;          // TRI only: operand is lower-triangular (stored col > stored row reads as 0)
+
+    __device__ __forceinline__ void init(const double* __restrict__ P, long long ld, int x0, int tid, bool msk) {
+        mask = msk;
+        if (KC) {
+            constexpr int CPR = G_BK / 2;  // chunks per row
+            const int row = tid / CPR, ch = tid % CPR;
+            g0 = P + (long long)(x0 + row) * ld + ch * 2;
+            step = (long long)(G_THREADS / CPR) * ld;
+            soff = (uint32_t)(row * G_LDK + ch * 2) * 8u;
+            adv = G_BK;
+            r0 = x0 + row;
+            c0 = ch * 2;
+        } else {
+            const int krow = tid >> 6, ch = tid & 63;
+            g0 = P + (long long)krow * ld + x0 + ch * 2;
+            step = 4 * ld;
+            soff = (uint32_t)(krow * G_LDM + ch * 2) * 8u;
+            adv = (long long)G_BK * ld;
+            r0 = krow;
+            c0 = x0 + ch * 2;
+        }
+    }
+    // copy k-tile `kt` into the tile at shared address `sbase`, then advance
+    __device__ __forceinline__ void load(uint32_t sbase, int kt) {
+        constexpr int CPR = G_BK / 2;
+#pragma unroll
+        for (int i = 0; i < G_NCH; ++i) {
+            const uint32_t dst = sbase + soff + (uint32_t)i * (KC ? (G_THREADS / CPR) * G_LDK * 8u : 4u * G_LDM * 8u);
+            int bytes = 16;
+            if (TRI) {
+                if (mask) {
+                    const int gr = KC ? r0 + i * (G_THREADS / CPR) : r0 + i * 4 + kt * G_BK;
+                    const int gc = KC ? c0 + kt * G_BK : c0;
+                    int v = gr - gc + 1;
+                    v = v < 0 ? 0 : (v > 2 ? 2 : v);
+                    bytes = v * 8;
+                }
+            }
+            cp_async16s(dst, g0 + i * step, bytes);
+        }
+        g0 += adv;
+    }
+};
+
+template <bool A_KC, bool B_KC, bool TRI>
 __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(const GemmArgs p) {
     extern __shared__ __align__(16) double smem[];
 
@@ -117,6 +153,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(const GemmArgs 
     const double* __restrict__ B = p.B + (long long)blockIdx.z * p.sB;
     double* __restrict__ C = p.C + (long long)blockIdx.z * p.sC;
 
+    TileLoader<A_KC, TRI> la;
+    TileLoader<B_KC, TRI> lb;
+    la.init(A, p.lda, m0, tid, TRI && p.triA);
+    lb.init(B, p.ldb, n0, tid, TRI && p.triB);
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(smem);
+
     double acc[8][4][2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -125,14 +167,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(const GemmArgs 
 
     const int nk = p.K / G_BK;
 
+    auto issue = [&](int kt) {
+        const uint32_t sb = sm0 + (uint32_t)(kt % G_STAGES) * (G_STAGE * 8u);
+        la.load(sb, kt);
+        lb.load(sb + G_TILE * 8u, kt);
+    };
+
     // ---- prologue ---------------------------------------------------------
 #pragma unroll
     for (int s = 0; s < G_STAGES - 1; ++s) {
-        if (s < nk) {
-            double* sa = smem + s * G_STAGE;
-            load_tile<A_KC>(sa, A, p.lda, m0, s * G_BK, p.triA, tid);
-            load_tile<B_KC>(sa + G_TILE, B, p.ldb, n0, s * G_BK, p.triB, tid);
-        }
+        if (s < nk) issue(s);
         cp_async_commit();
     }
 
@@ -140,21 +184,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(const GemmArgs 
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<G_STAGES - 2>();
         __syncthreads();
-        {
-            const int nt = kt + G_STAGES - 1;
-            if (nt < nk) {
-                double* sa = smem + (nt % G_STAGES) * G_STAGE;
-                load_tile<A_KC>(sa, A, p.lda, m0, nt * G_BK, p.triA, tid);
-                load_tile<B_KC>(sa + G_TILE, B, p.ldb, n0, nt * G_BK, p.triB, tid);
-            }
-            cp_async_commit();
-        }
         const double* sa = smem + (kt % G_STAGES) * G_STAGE;
         const double* sb = sa + G_TILE;
         const double* pa = A_KC ? sa + (wm * 64 + g) * G_LDK + t : sa + t * G_LDM + wm * 64 + g;
         const double* pb = B_KC ? sb + (wn * 32 + g) * G_LDK + t : sb + t * G_LDM + wn * 32 + g;
+        const int nt = kt + G_STAGES - 1;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+        for (int kk = 0; kk < G_BK / 4; ++kk) {
             double af[8], bf[4];
 #pragma unroll
             for (int i = 0; i < 8; ++i) af[i] = A_KC ? pa[i * 8 * G_LDK + kk * 4] : pa[kk * 4 * G_LDM + i * 8];
@@ -164,6 +200,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(const GemmArgs 
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            // the two warps of an SM sub-partition (wm = 0 / 1) refill the ring at
+            // different k4 steps, so one of them is always issuing DMMAs
+            if (kk == (wm ? G_BK / 8 : 0)) {
+                if (nt < nk) issue(nt);
+                cp_async_commit();
+            }
         }
     }
     cp_async_wait<0>();
