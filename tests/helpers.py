@@ -98,5 +98,8 @@ def cpu_copy(m):
 
 def rel_err(a, b):
     a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.numel() == 0:
+        return 0.0
     den = max(b.abs().max().item(), 1e-300)
     return (a - b).abs().max().item() / den

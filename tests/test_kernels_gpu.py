@@ -1,0 +1,239 @@
+"""GPU: every C-ABI entry point against torch float64 on the same device / the CPU oracle,
+including ragged shapes, failure reporting and size-independent properties at large n."""
+import math
+
+import pytest
+import torch
+
+from oracle import plmc_oracle as O
+from projected_lmc_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float64).to(DEV)
+
+
+def spd(b, n, seed=0):
+    X = rnd(b, n, n + 32, seed=seed)
+    return X @ X.transpose(1, 2) / n + torch.eye(n, dtype=torch.float64, device=DEV)
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2, 3])
+@pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (-0.5, 1.0), (2.0, -0.25)])
+def test_gemm_layouts(layout, alpha, beta):
+    M, N, K, b = 256, 384, 160, 3
+    a_mc, b_nc = bool(layout & 2), bool(layout & 1)
+    A = rnd(b, K, M, seed=1) if a_mc else rnd(b, M, K, seed=1)
+    B = rnd(b, K, N, seed=2) if b_nc else rnd(b, N, K, seed=2)
+    C = rnd(b, M, N, seed=3)
+    opA = A.transpose(1, 2) if a_mc else A
+    opB = B if b_nc else B.transpose(1, 2)
+    ref = alpha * opA @ opB + beta * C
+    ops.gemm(layout, A, B, C, M, N, K, alpha=alpha, beta=beta)
+    assert (C - ref).abs().max().item() < 1e-11
+
+
+def test_gemm_beta_zero_ignores_nan_in_c():
+    A, B = rnd(1, 128, 128, seed=1), rnd(1, 128, 128, seed=2)
+    C = torch.full((1, 128, 128), float("nan"), dtype=torch.float64, device=DEV)
+    ops.gemm(0, A, B, C, 128, 128, 128)
+    assert torch.isfinite(C).all()
+
+
+def test_gemm_lower_only_and_triangular_masks():
+    n = 384
+    P = rnd(2, n, 256, seed=4)
+    C0 = rnd(2, n, n, seed=5)
+    C = C0.clone()
+    ops.gemm(0, P, P, C, n, n, 256, alpha=-1.0, beta=1.0, lower=True)
+    ref = C0 - P @ P.transpose(1, 2)
+    for i in range(3):
+        for j in range(3):
+            blk = (slice(None), slice(128 * i, 128 * i + 128), slice(128 * j, 128 * j + 128))
+            if i >= j:
+                assert (C[blk] - ref[blk]).abs().max().item() < 1e-11
+            else:
+                assert torch.equal(C[blk], C0[blk])           # strictly-upper tiles untouched
+    # triangular operands: garbage (NaN) above the diagonal must never be read
+    T = rnd(1, 128, 128, seed=6)
+    Tn = T.clone()
+    Tn[0][torch.triu(torch.ones(128, 128, dtype=torch.bool, device=DEV), 1)] = float("nan")
+    Bm = rnd(1, 128, 256, seed=7)
+    out = torch.empty_like(Bm)
+    ops.gemm(3, Tn, Bm, out, 128, 256, 128, triA=True)        # out = tril(T)^T @ B
+    assert (out - torch.tril(T).transpose(1, 2) @ Bm).abs().max().item() < 1e-11
+    out2 = torch.empty(1, 128, 128, dtype=torch.float64, device=DEV)
+    ops.gemm(3, Tn, Tn, out2, 128, 128, 128, triA=True, triB=True)   # tril(T)^T tril(T)
+    assert (out2 - torch.tril(T).transpose(1, 2) @ torch.tril(T)).abs().max().item() < 1e-11
+
+
+@pytest.mark.parametrize("n,b", [(128, 1), (256, 5), (640, 2), (1152, 3)])
+def test_potrf_solve_trtri_lauum(n, b):
+    K0 = spd(b, n, seed=n)
+    K = K0.clone()
+    dinv = ops.alloc_dinv(n, b, DEV)
+    info = torch.full((b,), 7, dtype=torch.int32, device=DEV)
+    ops.potrf(K, dinv, info)
+    assert info.tolist() == [0] * b
+    Lref = torch.linalg.cholesky(K0)
+    assert (torch.tril(K) - Lref).abs().max().item() < 1e-12
+    y = rnd(b, n, seed=11)
+    z, alpha, quad, logdet = ops.solve_logdet(K, dinv, y, n)
+    zref = torch.linalg.solve_triangular(Lref, y.unsqueeze(-1), upper=False).squeeze(-1)
+    assert (z - zref).abs().max().item() < 1e-11
+    assert (alpha - torch.cholesky_solve(y.unsqueeze(-1), Lref).squeeze(-1)).abs().max().item() < 1e-11
+    assert torch.allclose(quad, zref.pow(2).sum(-1), rtol=1e-13)
+    assert torch.allclose(logdet, 2 * torch.log(torch.diagonal(Lref, dim1=1, dim2=2)).sum(-1), rtol=1e-13, atol=1e-12)
+    ops.trtri(K, dinv)
+    assert (torch.tril(K) - torch.linalg.inv(Lref)).abs().max().item() < 1e-11
+    ops.lauum(K)
+    assert (torch.tril(K) - torch.tril(torch.linalg.inv(K0))).abs().max().item() < 1e-10
+
+
+def test_potrf_reports_first_bad_pivot_per_batch_member():
+    n = 384
+    K = spd(3, n, seed=2)
+    K[1, 200, 200] = -5.0          # member 1 loses positive definiteness at pivot 201 (1-based)
+    K[2, 0, 0] = 0.0               # member 2 fails at the very first pivot
+    K0 = K.clone()
+    dinv = ops.alloc_dinv(n, 3, DEV)
+    info = torch.zeros(3, dtype=torch.int32, device=DEV)
+    ops.potrf(K, dinv, info)
+    got = info.tolist()
+    _, ref_info = torch.linalg.cholesky_ex(K0)
+    assert got[0] == 0 and got[1] == ref_info[1].item() == 201 and got[2] == ref_info[2].item() == 1
+    assert (torch.tril(K[0]) - torch.linalg.cholesky(K0[0])).abs().max().item() < 1e-12   # healthy member unaffected
+
+
+@pytest.mark.parametrize("op", [0, 1, 2, 3])
+def test_trsm_ops(op):
+    n, m, b = 512, 256, 2
+    K0 = spd(b, n, seed=3)
+    K = K0.clone()
+    dinv = ops.alloc_dinv(n, b, DEV)
+    info = torch.zeros(b, dtype=torch.int32, device=DEV)
+    ops.potrf(K, dinv, info)
+    L = torch.tril(K)
+    B0 = rnd(b, m, n, seed=5) if op in (0, 1) else rnd(b, n, m, seed=5)
+    B = B0.clone()
+    ops.trsm(op, K, dinv, B, alpha=-0.5)
+    if op == 0:
+        ref = torch.linalg.solve_triangular(L.transpose(1, 2), -0.5 * B0, upper=True, left=False)
+    elif op == 1:
+        ref = torch.linalg.solve_triangular(L, -0.5 * B0, upper=False, left=False)
+    elif op == 2:
+        ref = torch.linalg.solve_triangular(L, -0.5 * B0, upper=False)
+    else:
+        ref = torch.linalg.solve_triangular(L.transpose(1, 2), -0.5 * B0, upper=True)
+    assert (B - ref).abs().max().item() < 1e-10
+
+
+@pytest.mark.parametrize("n,p,q", [(1, 1, 1), (63, 7, 4), (1000, 50, 10), (4097, 65, 33), (513, 500, 32)])
+def test_projection_fwd_bwd(n, p, q):
+    Y, T = rnd(n, p, seed=1), rnd(p, q, seed=2)
+    TY = ops.project_fwd(Y, T)
+    assert TY.shape == (q, n)
+    assert (TY - (Y @ T).T).abs().max().item() < 1e-11 * max(1, p)
+    G = rnd(q, n, seed=3)
+    dT = ops.project_bwd(Y, G)
+    assert (dT - Y.T @ G.T).abs().max().item() < 1e-10 * max(1.0, math.sqrt(n))
+
+
+def _oracle_params(kind, ell, noise, os_=None):
+    q, d = ell.shape
+    inv = lambda v: v + torch.log(-torch.expm1(-v))          # inverse softplus
+    return O.OracleParams(raw_lengthscale=inv(ell.cpu())[:, None, :], raw_noise=inv(noise.cpu())[:, None],
+                          noise_lower=0.0, kernel=kind, raw_outputscale=None if os_ is None else inv(os_.cpu()))
+
+
+@pytest.mark.parametrize("kind,kid", [("rbf", 0), ("matern52", 1), ("matern32", 2), ("matern12", 3)])
+@pytest.mark.parametrize("n,d,with_os", [(100, 1, False), (300, 6, True), (257, 21, False)])
+def test_gram_and_cross_gram_vs_oracle(kind, kid, n, d, with_os):
+    q = 3
+    g = torch.Generator().manual_seed(n + d)
+    X = (torch.rand(n, d, generator=g, dtype=torch.float64) * 2 - 1)
+    ell = torch.rand(q, d, generator=g, dtype=torch.float64) + 0.4
+    noise = torch.rand(q, generator=g, dtype=torch.float64) * 0.3 + 0.05
+    os_ = (torch.rand(q, generator=g, dtype=torch.float64) + 0.5) if with_os else None
+    Xg, ellg, ng = X.to(DEV), ell.to(DEV), noise.to(DEV)
+    osg = None if os_ is None else os_.to(DEV)
+    np_ = ops.npad(n)
+    Z, zn = ops.scale_inputs(Xg, ops.col_mean(Xg), ellg, np_)
+    K = torch.full((q, np_, np_), float("nan"), dtype=torch.float64, device=DEV)
+    ops.gram(Z, zn, kid, osg, ng, K, n)
+    p = _oracle_params(kind, ell, noise, os_)
+    Kref = O.gram(p, X, training=False) + torch.diag_embed(noise[:, None].expand(-1, n))
+    low = torch.tril(torch.ones(n, n, dtype=torch.bool))
+    got = K[:, :n, :n].cpu()
+    tol = 1e-7 if kind == "matern12" else 1e-12       # nu=1/2: sqrt amplifies the expansion's round-off near r=0
+    assert (got - Kref)[:, low].abs().max().item() < tol
+    # identity padding, lower part
+    if np_ > n:
+        pad = K[:, n:, :].cpu()
+        eye = torch.zeros_like(pad)
+        eye[:, torch.arange(np_ - n), n + torch.arange(np_ - n)] = 1.0
+        lowpad = torch.tril(torch.ones(np_, np_, dtype=torch.bool))[n:, :]
+        assert torch.equal(pad[:, lowpad], eye[:, lowpad])
+    # cross Gram against test points
+    ns = 150
+    Xs = torch.rand(ns, d, generator=g, dtype=torch.float64) * 2 - 1
+    mt = ops.npad(ns)
+    Zt, znt = ops.scale_inputs(Xs.to(DEV), ops.col_mean(Xg), ellg, mt)
+    Kx = torch.empty((q, np_, mt), dtype=torch.float64, device=DEV)
+    ops.cross_gram(Z, zn, Zt, znt, kid, osg, Kx, n, mt)
+    Kxref = O.gram(p, X, Xs, training=False)
+    assert (Kx[:, :n, :ns].cpu() - Kxref).abs().max().item() < tol
+    assert Kx[:, n:, :].abs().max().item() == 0.0 if np_ > n else True
+
+
+def test_prediction_epilogues():
+    q, n, ns, p = 5, 300, 200, 37
+    np_, mt = ops.npad(n), ops.npad(ns)
+    Kx = rnd(q, np_, mt, seed=1)
+    Kx[:, n:, :] = 0
+    alpha = rnd(q, n, seed=2)
+    lm = ops.latent_mean(Kx, alpha, n, mt)
+    assert (lm[:, :ns] - torch.einsum("qi,qij->qj", alpha, Kx[:, :n, :ns])).abs().max().item() < 1e-11
+    os_ = torch.rand(q, dtype=torch.float64, device=DEV) + 0.5
+    lv = ops.latent_var(Kx, os_, mt)
+    assert (lv[:, :ns] - (os_[:, None] - Kx[:, :, :ns].pow(2).sum(1))).abs().max().item() < 1e-10
+    H = rnd(q, p, seed=3)
+    va = torch.rand(p, dtype=torch.float64, device=DEV)
+    mean = torch.empty(ns, p, dtype=torch.float64, device=DEV)
+    var = torch.empty_like(mean)
+    ops.mix_tasks(lm, lv, H, va, mean, var, ns)
+    assert (mean - lm[:, :ns].T @ H).abs().max().item() < 1e-11
+    assert (var - (lv[:, :ns].T @ H.pow(2) + va)).abs().max().item() < 1e-10
+    ops.mix_tasks(lm, lv, H, va, mean, var, ns, accumulate=True)
+    assert (mean - 2 * lm[:, :ns].T @ H).abs().max().item() < 1e-11
+
+
+def test_large_n_properties():
+    """n = 8192 (beyond a quick CPU oracle): residual, symmetry and determinant properties."""
+    n, q, d = 8192, 2, 5
+    g = torch.Generator().manual_seed(0)
+    X = (torch.rand(n, d, generator=g, dtype=torch.float64) * 2 - 1).to(DEV)
+    ell = torch.full((q, d), 0.7, dtype=torch.float64, device=DEV)
+    noise = torch.tensor([0.3, 0.05], dtype=torch.float64, device=DEV)
+    Z, zn = ops.scale_inputs(X, ops.col_mean(X), ell, n)
+    K = torch.empty((q, n, n), dtype=torch.float64, device=DEV)
+    ops.gram(Z, zn, 1, None, noise, K, n)
+    Kfull = torch.tril(K) + torch.tril(K, -1).transpose(1, 2)
+    dinv = ops.alloc_dinv(n, q, DEV)
+    info = torch.zeros(q, dtype=torch.int32, device=DEV)
+    ops.potrf(K, dinv, info)
+    assert info.tolist() == [0, 0]
+    y = rnd(q, n, seed=4)
+    z, alpha, quad, logdet = ops.solve_logdet(K, dinv, y, n)
+    resid = (Kfull @ alpha.unsqueeze(-1)).squeeze(-1) - y
+    assert resid.abs().max().item() < 1e-9 * y.abs().max().item() * 10
+    assert torch.allclose(quad, (alpha * y).sum(-1), rtol=1e-10)              # y^T K^-1 y two ways
+    assert torch.allclose(logdet, torch.linalg.slogdet(Kfull)[1], rtol=1e-10)
+    ops.potri(K, dinv)
+    Kinv = torch.tril(K) + torch.tril(K, -1).transpose(1, 2)
+    v = rnd(q, n, 3, seed=5)
+    assert ((Kfull @ (Kinv @ v)) - v).abs().max().item() < 1e-8               # K K^-1 v = v

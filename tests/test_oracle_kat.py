@@ -1,0 +1,82 @@
+"""Known-answer tests of the oracle (CPU): dependency-free identities, see oracle/kat.py."""
+import warnings
+
+import pytest
+import torch
+
+from oracle import kat
+from oracle import plmc_oracle as O
+
+from .helpers import VARIANTS, make_model, oracle_params, rel_err, synth
+
+
+@pytest.mark.parametrize("variant", ["PLMC", "PLMC_fast", "BDN_diag", "BDN_full", "M_diag", "oilmm", "nonbulk_tri"])
+@pytest.mark.parametrize("kernel", ["rbf", "matern52"])
+def test_kat1_mll_equals_dense_multitask_loglik(variant, kernel):
+    X, Y, _, _ = synth(40, 2, 6, 3, seed=3)
+    m = make_model(X, Y, 3, variant=variant, kernel=kernel)
+    with torch.no_grad():
+        p = oracle_params(m)
+        lhs = O.mll(p, X, Y) * X.shape[0]
+        rhs = kat.dense_log_likelihood(p, X, Y)
+    assert abs(lhs - rhs) <= 1e-10 * abs(rhs), (lhs.item(), rhs.item())
+
+
+@pytest.mark.parametrize("variant", ["PLMC", "PLMC_fast", "BDN_diag"])
+@pytest.mark.parametrize("kernel,os_", [("rbf", False), ("matern52", True)])
+def test_kat2_prediction_equals_dense_posterior(variant, kernel, os_):
+    X, Y, Xs, _ = synth(36, 2, 5, 2, seed=4, ns=7)
+    m = make_model(X, Y, 2, variant=variant, kernel=kernel, outputscales=os_)
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        p = oracle_params(m)
+        mean, var_f, _ = O.predict(p, X, Y, Xs)
+        mean_d, var_d = kat.dense_posterior(p, X, Y, Xs)
+    assert rel_err(mean, mean_d) < 1e-10
+    assert rel_err(var_f - p.eps, var_d) < 1e-9
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "matern52", "matern32", "matern12"])
+@pytest.mark.parametrize("os_", [False, True])
+def test_kat3_analytic_gradients_equal_autograd(kernel, os_):
+    torch.manual_seed(0)
+    n, d, q = 30, 3, 2
+    X = torch.rand(n, d) * 2 - 1
+    TY = torch.randn(q, n, requires_grad=True)
+    ell = (torch.rand(q, d) + 0.5).requires_grad_()
+    osv = (torch.rand(q) + 0.5).requires_grad_() if os_ else None
+    noise = (torch.rand(q) * 0.2 + 0.05).requires_grad_()
+    K = O.base_kernel(kernel, X, X, ell[:, None, :], zero_diag=False)
+    if os_:
+        K = K * osv[:, None, None]
+    K = K + torch.diag_embed(noise[:, None].expand(-1, n))
+    lp = O.mvn_log_prob(K, TY).sum()
+    lp.backward()
+    g_ell, g_os, g_noise, g_ty = kat.analytic_latent_grads(kernel, X, ell.detach(), None if osv is None else osv.detach(),
+                                                           noise.detach(), TY.detach())
+    # nu = 1/2 is not differentiable at r = 0: autograd through the expansion-based distance picks up
+    # O(1e-7) round-off from the diagonal (sqrt of ~1e-15), the closed form treats it as exactly 0
+    # (its training-mode Gram diagonal is exp(-sqrt(round-off)) = 1 - O(1e-8) instead of 1).
+    tol = 1e-5 if kernel == "matern12" else 1e-10
+    assert rel_err(g_ell, ell.grad) < tol
+    assert rel_err(g_noise, noise.grad) < tol
+    assert rel_err(g_ty, TY.grad) < tol
+    if os_:
+        assert rel_err(g_os, osv.grad) < tol
+
+
+def test_psd_safe_cholesky_jitter_only_on_failing_members():
+    A = torch.eye(4).repeat(2, 1, 1)
+    A[1, 3, 3] = -1e-9                      # second batch member is not PD
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        L = O.psd_safe_cholesky(A, max_tries=3)
+    assert len(w) >= 1
+    assert torch.allclose(L[0], torch.eye(4))          # untouched member got no jitter
+    assert L[1, 3, 3] > 0
+    with pytest.raises(RuntimeError):
+        bad = torch.eye(3)
+        bad[2, 2] = -1.0
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            O.psd_safe_cholesky(bad[None], max_tries=3)

@@ -19,7 +19,7 @@ GRAD_TOL = 1e-7
 PRED_TOL = 1e-7
 
 
-def run_case(n, d, p, q, variant, kernel, outputscales=False, ns=37, seed=0):
+def run_case(n, d, p, q, variant, kernel, outputscales=False, ns=37, seed=0, grad_tol=GRAD_TOL, mll_tol=MLL_TOL):
     X, Y, Xs, _ = synth(n, d, p, q, seed=seed, ns=ns)
     m = make_model(X, Y, q, variant=variant, kernel=kernel, outputscales=outputscales, seed=seed)
     mc = cpu_copy(m)
@@ -34,7 +34,7 @@ def run_case(n, d, p, q, variant, kernel, outputscales=False, ns=37, seed=0):
     op = oracle_params(mc)
     ref = -O.mll(op, X, Y)
     ref.backward()
-    assert abs(loss.item() - ref.item()) <= MLL_TOL * abs(ref.item()), (loss.item(), ref.item())
+    assert abs(loss.item() - ref.item()) <= mll_tol * abs(ref.item()), (loss.item(), ref.item())
     ref_grads = dict(mc.named_parameters())
     for name, prm in m.named_parameters():
         g_ref = ref_grads[name].grad
@@ -42,7 +42,7 @@ def run_case(n, d, p, q, variant, kernel, outputscales=False, ns=37, seed=0):
             assert prm.grad is None or prm.grad.abs().max().item() == 0.0, name
             continue
         assert prm.grad is not None, name
-        assert rel_err(prm.grad, g_ref) <= GRAD_TOL, (name, prm.grad.cpu(), g_ref)
+        assert rel_err(prm.grad, g_ref) <= grad_tol, (name, prm.grad.cpu(), g_ref)
 
     # prediction
     m.eval()
@@ -68,7 +68,11 @@ def test_variants_small(variant, kernel):
 
 @pytest.mark.parametrize("kernel", ["matern32", "matern12"])
 def test_other_matern(kernel):
-    run_case(n=90, d=2, p=5, q=2, variant="PLMC", kernel=kernel)
+    # nu = 1/2 is not differentiable at r = 0: the reference's training-mode Gram diagonal is
+    # exp(-sqrt(round-off)) = 1 - O(1e-8) and its autograd carries the same noise; the CUDA path uses exactly 1
+    loose = kernel == "matern12"
+    run_case(n=90, d=2, p=5, q=2, variant="PLMC", kernel=kernel, grad_tol=(1e-5 if loose else GRAD_TOL),
+             mll_tol=(1e-6 if loose else MLL_TOL))
 
 
 def test_outputscales():
