@@ -148,15 +148,16 @@ def dmma_peak_tflops():
     return best
 
 
-def oracle_iteration_time(cfg, n_s, steps, warmup):
-    """The reference's algorithm (Cholesky-forced gpytorch semantics, restated in oracle/) on the host cores."""
+def oracle_iteration_time(cfg, n_s, steps, warmup, world=1):
+    """The reference's algorithm (Cholesky-forced gpytorch semantics, restated in oracle/) on the host cores.
+    `world` scales the model like the GPU arm does (4 latents / 7 tasks per GPU)."""
     from oracle import plmc_oracle as O
     from tests.helpers import oracle_params
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    X, Y = make_data(n_s, cfg["d"], cfg["p"], cfg["q"], seed=1)
-    m = build_model(X, Y, cfg["q"], cfg["kernel"])
+    X, Y = make_data(n_s, cfg["d"], cfg["p"] * world, cfg["q"] * world, seed=1)
+    m = build_model(X, Y, cfg["q"] * world, cfg["kernel"])
     times = []
     for it in range(warmup + steps):
         for prm in m.parameters():
@@ -176,15 +177,16 @@ def run_reference(args, cfg):
         return
     n = args.n or cfg["n"]
     n_s = min(CPU_SAMPLE_N, n)
-    t, cores = oracle_iteration_time(cfg, n_s, max(1, args.steps), max(1, min(args.warmup, 1)))
+    world = max(1, args.gpus)
+    t, cores = oracle_iteration_time(cfg, n_s, max(1, args.steps), max(1, min(args.warmup, 1)), world)
     scale = (n_s / n) ** 3
-    value = (1.0 / t) * scale * 1.0
+    value = (world / t) * scale          # one step of the N-GPU workload = N four-latent model iterations
     sample = (f"oracle (pure-torch restatement of the reference's Cholesky-forced path; gpytorch is not installable) "
-              f"fwd+bwd at n={n_s}, d={cfg['d']}, p={cfg['p']}, q={cfg['q']}, {cfg['kernel']}: {t:.3f} s/iter on "
-              f"{cores} host threads; it/s scaled by (n_s/n)^3 = {scale:.3e} to n={n}")
+              f"fwd+bwd at n={n_s}, d={cfg['d']}, p={cfg['p'] * world}, q={cfg['q'] * world}, {cfg['kernel']}: "
+              f"{t:.3f} s/iter on {cores} host threads; it/s scaled by (n_s/n)^3 = {scale:.3e} to n={n}")
     line = {
         "impl": "reference", "metric": "train_iters_per_sec", "value": value, "unit": "it/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * world / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, cfg, args.gpus),
         "cpu_baseline": {"value": value, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample},

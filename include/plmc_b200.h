@@ -88,6 +88,14 @@ int plmc_trsm_batched(int op, const double* L, long long ld, long long stride, l
 int plmc_solve_logdet(const double* L, long long ld, long long stride, long long n, long long npad, int batch,
                       const double* dinv, const double* y, long long ldy, double* rhs, double* z, double* alpha,
                       long long ldv, double* quad, double* logdet, void* stream);
+/* The same four outputs from the EXPLICIT inverse factor (training step: trtri has
+ * already run): z = Linv y, alpha = Linv^T z, quad, logdet = -2 sum log Linv_ii.
+ * Two HBM passes over the lower triangle instead of two blocked solves.
+ * ws: plmc_trmv_ws(npad, batch) bytes.                                           */
+long long plmc_trmv_ws(long long npad, int batch);
+int plmc_trmv_solve_logdet(const double* Linv, long long ld, long long stride, long long n, long long npad,
+                           int batch, const double* y, long long ldy, double* ws, double* z, double* alpha,
+                           long long ldv, double* quad, double* logdet, void* stream);
 /* L -> inv(L) (lower) in place */
 int plmc_trtri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
                        void* stream);

@@ -36,6 +36,8 @@ _SIGNATURES = {
     "plmc_potrf_batched": [P, LL, LL, LL, I, P, P, P],
     "plmc_trsm_batched": [I, P, LL, LL, LL, I, P, P, LL, LL, LL, D, P],
     "plmc_solve_logdet": [P, LL, LL, LL, LL, I, P, P, LL, P, P, P, LL, P, P, P],
+    "plmc_trmv_ws": [LL, I],
+    "plmc_trmv_solve_logdet": [P, LL, LL, LL, LL, I, P, LL, P, P, P, LL, P, P, P],
     "plmc_trtri_batched": [P, LL, LL, LL, I, P, P],
     "plmc_lauum_batched": [P, LL, LL, LL, I, P],
     "plmc_potri_batched": [P, LL, LL, LL, I, P, P],
@@ -49,7 +51,7 @@ _SIGNATURES = {
     "plmc_peak_dfma": [I, I, LL, P, P],
     "plmc_peak_copy": [P, P, LL, P],
 }
-_RET_LL = {"plmc_npad", "plmc_dinv_bytes", "plmc_project_bwd_ws", "plmc_grad_ws"}
+_RET_LL = {"plmc_npad", "plmc_dinv_bytes", "plmc_project_bwd_ws", "plmc_grad_ws", "plmc_trmv_ws"}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

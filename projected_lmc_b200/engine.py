@@ -108,12 +108,18 @@ class LatentEngine:
         self._gram_potrf(ws, Z, zn, kid, os_, noise, n, max_tries)
         mark("retry")
         K, dinv = ws["K"], ws["dinv"]
-        z, alpha, quad, logdet = ops.solve_logdet(K, dinv, TY, n, ws["rhs"])
+        if not need_grad:
+            z, alpha, quad, logdet = ops.solve_logdet(K, dinv, TY, n, ws["rhs"])
+            mark("solve_logdet")
+            return -0.5 * (quad + logdet + n * math.log(2 * math.pi)), None
+        # training step: the inverse factor is needed anyway, so the single-RHS solves
+        # become two HBM-bound triangular mat-vecs with L^-1 (no dependency chain)
+        ops.trtri(K, dinv)
+        mark("potri")
+        z, alpha, quad, logdet = ops.trmv_solve_logdet(K, TY, n, ws["rhs"])
         lp = -0.5 * (quad + logdet + n * math.log(2 * math.pi))
         mark("solve_logdet")
-        if not need_grad:
-            return lp, None
-        ops.potri(K, dinv)
+        ops.lauum(K)
         mark("potri")
         g_ell, g_os, g_noise = ops.grad_sweep(K, alpha, Z, zn, ell, kid, os_, n)
         mark("grad_sweep")

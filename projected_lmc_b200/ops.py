@@ -76,6 +76,26 @@ def solve_logdet(L, dinv, y, n, rhs=None):
     return z, alpha, quad, logdet
 
 
+def trmv_solve_logdet(Linv, y, n, ws=None):
+    """Same outputs as solve_logdet, from the explicit inverse factor Linv [batch, npad, ld]."""
+    b, np_, _ = Linv.shape
+    dev = Linv.device
+    if ws is None:
+        ws = torch.empty((b, 128, np_), dtype=torch.float64, device=dev)
+    z = torch.empty((b, n), dtype=torch.float64, device=dev)
+    alpha = torch.empty((b, n), dtype=torch.float64, device=dev)
+    quad = torch.empty((b,), dtype=torch.float64, device=dev)
+    logdet = torch.empty((b,), dtype=torch.float64, device=dev)
+    check(
+        lib().plmc_trmv_solve_logdet(
+            ptr(Linv), Linv.stride(1), Linv.stride(0), n, np_, b, ptr(y), y.stride(0), ptr(ws), ptr(z), ptr(alpha), n,
+            ptr(quad), ptr(logdet), stream(),
+        ),
+        "trmv_solve_logdet",
+    )
+    return z, alpha, quad, logdet
+
+
 def trtri(L, dinv):
     b, np_, _ = L.shape
     check(lib().plmc_trtri_batched(ptr(L), L.stride(1), L.stride(0), np_, b, ptr(dinv), stream()), "trtri")
