@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="override n (debug only; reported in config)")
+    ap.add_argument("--points", dest="n", type=int, default=0, help="override n (debug only; reported in config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()

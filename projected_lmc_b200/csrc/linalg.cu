@@ -1,97 +1,7 @@
 #include "linalg.cuh"
+#include "potrf_leaf.cuh"
 
 namespace plmc {
-
-// ---------------------------------------------------------------------------
-// 128x128 Cholesky leaf, one CTA per batch member, matrix resident in shared
-// memory.  Replaces the inner potrf of torch.linalg.cholesky_ex that
-// gpytorch's psd_safe_cholesky calls (reached from projected_lmc.py:1201).
-// Also writes inv(L_leaf) to Dinv so TRSM leaves become GEMMs.
-// ---------------------------------------------------------------------------
-constexpr int LEAF = 128;
-constexpr int LEAF_LD = 129;
-constexpr int LEAF_THREADS = 256;
-constexpr int LEAF_SMEM = (LEAF * LEAF_LD + LEAF) * 8;
-
-__global__ void __launch_bounds__(LEAF_THREADS, 1)
-    potrf_leaf_kernel(double* __restrict__ Abase, long long ld, long long sA, double* __restrict__ Dbase,
-                      long long sD, int* __restrict__ info, int row_off) {
-    extern __shared__ __align__(16) double S[];
-    double* xd = S + LEAF * LEAF_LD;
-    const int b = blockIdx.x;
-    const int tid = threadIdx.x;
-    double* A = Abase + (long long)b * sA;
-    double* D = Dbase + (long long)b * sD;
-
-    for (int idx = tid; idx < LEAF * LEAF; idx += LEAF_THREADS) {
-        const int r = idx >> 7, c = idx & 127;
-        if (c <= r) S[r * LEAF_LD + c] = A[(long long)r * ld + c];
-    }
-
-    // right-looking, unscaled columns (scaling deferred): one barrier per column
-    const int tx = tid & 15, ty = tid >> 4;
-    int fail = 0;
-    for (int j = 0; j < LEAF; ++j) {
-        __syncthreads();
-        const double d = S[j * LEAF_LD + j];
-        if (!(d > 0.0)) {
-            fail = j + 1;
-            break;
-        }
-        const double rd = 1.0 / d;
-        for (int i = j + 1 + ty; i < LEAF; i += 16) {
-            const double lij = S[i * LEAF_LD + j] * rd;
-            for (int k = j + 1 + tx; k <= i; k += 16) S[i * LEAF_LD + k] -= lij * S[k * LEAF_LD + j];
-        }
-    }
-    __syncthreads();
-    if (fail && tid == 0 && info[b] == 0) info[b] = row_off + fail;
-    // scale columns: L[i][j] = S[i][j] / sqrt(S[j][j])
-    for (int idx = tid; idx < LEAF * LEAF; idx += LEAF_THREADS) {
-        const int r = idx >> 7, c = idx & 127;
-        if (c < r) S[r * LEAF_LD + c] *= rsqrt(S[c * LEAF_LD + c]);
-    }
-    __syncthreads();
-    if (tid < LEAF) S[tid * LEAF_LD + tid] = sqrt(S[tid * LEAF_LD + tid]);
-    __syncthreads();
-
-    // write back L (lower part only)
-    for (int idx = tid; idx < LEAF * LEAF; idx += LEAF_THREADS) {
-        const int r = idx >> 7, c = idx & 127;
-        if (c <= r) A[(long long)r * ld + c] = S[r * LEAF_LD + c];
-    }
-
-    // inverse by forward substitution, 2 threads per column; column j of
-    // X = inv(L) is kept transposed in row j of the (free) upper triangle.
-    {
-        const int j = tid >> 1, h = tid & 1;
-        const int kmin = (tid >> 5) * 16;  // smallest column owned by this warp
-        if (h == 0) xd[j] = 1.0 / S[j * LEAF_LD + j];
-        __syncwarp();
-        for (int i = kmin + 1; i < LEAF; ++i) {
-            double s = 0.0;
-            for (int k = kmin + h; k < i; k += 2) {
-                if (k >= j) {
-                    const double xk = (k == j) ? xd[j] : S[j * LEAF_LD + k];
-                    s += S[i * LEAF_LD + k] * xk;
-                }
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (h == 0 && j < i) S[j * LEAF_LD + i] = -s / S[i * LEAF_LD + i];
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < LEAF * LEAF; idx += LEAF_THREADS) {
-        const int r = idx >> 7, c = idx & 127;
-        double v = 0.0;
-        if (c < r)
-            v = S[c * LEAF_LD + r];
-        else if (c == r)
-            v = xd[r];
-        D[r * LEAF + c] = v;
-    }
-}
 
 // copy Dinv leaves over the diagonal blocks (lower part) : final step of trtri
 __global__ void dinv_to_diag_kernel(double* __restrict__ Lbase, long long ld, long long sL,
