@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--points", dest="n", type=int, default=0, help="override n (debug only; reported in config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-predict", action="store_true")
+    ap.add_argument("--test-points", type=int, default=8192)
     return ap.parse_args()
 
 
@@ -298,6 +300,38 @@ def main():
         e2e = {"value": world / (float(ms2.item()) * 1e-3), "unit": "it/s",
                "h2d_bytes_per_step": (Xh.numel() + Yh.numel()) * 8, "d2h_bytes_per_step": 8}
 
+    # ---- prediction: batched predictive mean/variance on the same model (secondary metric) -------
+    predict = None
+    if not args.no_predict:
+        n_test = args.test_points
+        gt = torch.Generator().manual_seed(7)
+        Xs = (torch.rand(n_test, cfg["d"], generator=gt, dtype=torch.float64) * 2 - 1).to(dev)
+        model.eval()
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            barrier()
+            e0.record()
+            _ = model(Xs[:128])                      # factorise (cached afterwards) + one small tile
+            e1.record()
+            barrier()
+            fact_s = e0.elapsed_time(e1) * 1e-3
+            full_lik = model.full_likelihood()
+            e0.record()
+            pred = full_lik(model(Xs))
+            chk = float(pred.variance.sum().item() + pred.mean.sum().item())
+            e1.record()
+            barrier()
+        ms3 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+        pred_s = float(ms3.item()) * 1e-3
+        predict = {"points_per_sec": n_test / pred_s, "n_test": n_test, "seconds": pred_s,
+                   "factorisation_seconds_excluded": fact_s, "checksum": chk,
+                   "algorithmic_tflops": cfg["q"] * float(n) ** 2 * n_test / pred_s / 1e12,
+                   "note": "mean + variance [n_test, tasks] through model.eval(); full_likelihood(model(X*)); "
+                           "FLOP = q*n^2*n* (triangular solve), per GPU"}
+        model.train()
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
         q_loc = cfg["q"]
@@ -332,6 +366,7 @@ def main():
                 "peak": peaks.get("hbm_gbs"), "peak_source": peak_src, "unit": "GB/s",
             }],
             "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+            "predict": predict,
         }
         for r in line["roofline_secondary"]:
             r["frac"] = (r["achieved"] / r["peak"]) if (r["achieved"] and r["peak"]) else None

@@ -139,6 +139,11 @@ int plmc_gemm(int layout, const double* A, long long lda, long long sA, const do
 int plmc_peak_dmma(int blocks, int threads, long long iters, double* scratch, void* stream);
 int plmc_peak_dfma(int blocks, int threads, long long iters, double* scratch, void* stream);
 int plmc_peak_copy(const double* src, double* dst, long long n, void* stream);
+/* even warps run the DMMA loop (iters_mma x 16 x 512 FLOP per warp), odd warps the DFMA loop
+ * (iters_fma x 16 x 2 FLOP per thread): shows that on B200 the two share one FP64 datapath
+ * (measured sum 35-36 TFLOP/s for every mix), i.e. 37 TFLOP/s is the FP64 roof.          */
+int plmc_peak_mixed(int blocks, int threads, long long iters_mma, long long iters_fma, double* scratch,
+                    void* stream);
 
 #ifdef __cplusplus
 }

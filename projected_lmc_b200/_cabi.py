@@ -50,6 +50,7 @@ _SIGNATURES = {
     "plmc_peak_dmma": [I, I, LL, P, P],
     "plmc_peak_dfma": [I, I, LL, P, P],
     "plmc_peak_copy": [P, P, LL, P],
+    "plmc_peak_mixed": [I, I, LL, LL, P, P],
 }
 _RET_LL = {"plmc_npad", "plmc_dinv_bytes", "plmc_project_bwd_ws", "plmc_grad_ws", "plmc_trmv_ws"}
 

@@ -17,6 +17,7 @@
 namespace plmc {
 
 constexpr int GR_THREADS = 256;
+constexpr int GR_KC = 32;  // input-dimension chunk staged in shared memory by the Gram kernel
 
 __host__ __device__ inline int gram_lds(int dpad) { return ((dpad + 11) / 16) * 16 + 4; }
 
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1)
                 const double* __restrict__ os, const double* __restrict__ diag_add, double* __restrict__ Kout,
                 long long ld, long long stride, long long n, int dpad, int tiles_c) {
     extern __shared__ __align__(16) double sm[];
-    const int lds = gram_lds(dpad);
+    const int lds = gram_lds(dpad < GR_KC ? dpad : GR_KC);
     double* Zi = sm;
     double* Zj = sm + 128 * lds;
     double* ni = Zj + 128 * lds;
@@ -126,16 +127,10 @@ __global__ void __launch_bounds__(GR_THREADS, 1)
 
     const double* zr = Zr + ((long long)l * rows_pad_r + i0) * dpad;
     const double* zc = Zc + ((long long)l * rows_pad_c + j0) * dpad;
-    for (int idx = tid; idx < 128 * dpad; idx += GR_THREADS) {
-        const int r = idx / dpad, k = idx - r * dpad;
-        Zi[r * lds + k] = zr[idx];
-        Zj[r * lds + k] = zc[idx];
-    }
     if (tid < 128) {
         ni[tid] = znr[(long long)l * rows_pad_r + i0 + tid];
         nj[tid] = znc[(long long)l * rows_pad_c + j0 + tid];
     }
-    __syncthreads();
 
     double acc[8][4][2];
 #pragma unroll
@@ -145,48 +140,68 @@ __global__ void __launch_bounds__(GR_THREADS, 1)
 
     const double* pa = Zi + (wm * 64 + g) * lds + t;
     const double* pb = Zj + (wn * 32 + g) * lds + t;
-    for (int k0 = 0; k0 < dpad; k0 += 4) {
-        double af[8], bf[4];
+    // input dimensions in chunks of GR_KC columns (shared memory stays bounded for any d)
+    for (int kc0 = 0; kc0 < dpad; kc0 += GR_KC) {
+        const int kc = min(GR_KC, dpad - kc0);
+        __syncthreads();
+        for (int idx = tid; idx < 128 * kc; idx += GR_THREADS) {
+            const int r = idx / kc, k = idx - r * kc;
+            Zi[r * lds + k] = zr[r * dpad + kc0 + k];
+            Zj[r * lds + k] = zc[r * dpad + kc0 + k];
+        }
+        __syncthreads();
+        for (int k0 = 0; k0 < kc; k0 += 4) {
+            double af[8], bf[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) af[i] = pa[i * 8 * lds + k0];
+            for (int i = 0; i < 8; ++i) af[i] = pa[i * 8 * lds + k0];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bf[j] = pb[j * 8 * lds + k0];
+            for (int j = 0; j < 4; ++j) bf[j] = pb[j * 8 * lds + k0];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
     }
 
-    const double osl = os ? os[l] : 1.0;
-    const double dadd = (MODE == 0) ? diag_add[l] : 0.0;
-    double* Kl = Kout + (long long)l * stride;
+    // Stage the squared distances through a private shared-memory slab (slot e of thread tid at
+    // stage[e * 256 + tid]: conflict free, no barrier needed because every thread reads back only
+    // what it wrote).  The transcendental epilogue then runs as a ROLLED loop: fully unrolled it is
+    // ~100 KB of code and the kernel stalls on instruction fetch (ncu: stall_no_instruction 3.4/issue).
+    double* stage = nj + 128;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int rl = wm * 64 + i * 8 + g;
-        const long long gi = i0 + rl;
-        const double nri = ni[rl];
+        const double nri = ni[wm * 64 + i * 8 + g];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int cl = wn * 32 + j * 8 + 2 * t;
-            const long long gj = j0 + cl;
-            double v[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const long long gje = gj + e;
-                double s = nri + nj[cl + e] - 2.0 * acc[i][j][e];
-                s = fmax(s, 0.0);
-                if (MODE == 0) {
-                    if (gi == gje) s = 0.0;
-                    double kv = osl * kernel_value<KID>(s);
-                    if (gi == gje) kv += dadd;
-                    if (gi >= n || gje >= n) kv = (gi == gje) ? 1.0 : 0.0;
-                    v[e] = kv;
-                } else {
-                    v[e] = (gi < n) ? osl * kernel_value<KID>(s) : 0.0;
-                }
-            }
-            *reinterpret_cast<double2*>(Kl + gi * ld + gj) = make_double2(v[0], v[1]);
+            stage[((i * 4 + j) * 2 + 0) * GR_THREADS + tid] = fmax(nri + nj[cl] - 2.0 * acc[i][j][0], 0.0);
+            stage[((i * 4 + j) * 2 + 1) * GR_THREADS + tid] = fmax(nri + nj[cl + 1] - 2.0 * acc[i][j][1], 0.0);
         }
+    }
+    const double osl = os ? os[l] : 1.0;
+    const double dadd = (MODE == 0) ? diag_add[l] : 0.0;
+    double* Kl = Kout + (long long)l * stride;
+#pragma unroll 4
+    for (int pr = 0; pr < 32; ++pr) {
+        const int i = pr >> 2, j = pr & 3;
+        const long long gi = i0 + wm * 64 + i * 8 + g;
+        const long long gj = j0 + wn * 32 + j * 8 + 2 * t;
+        double v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const long long gje = gj + e;
+            double s = stage[(pr * 2 + e) * GR_THREADS + tid];
+            if (MODE == 0) {
+                if (gi == gje) s = 0.0;
+                double kv = osl * kernel_value<KID>(s);
+                if (gi == gje) kv += dadd;
+                if (gi >= n || gje >= n) kv = (gi == gje) ? 1.0 : 0.0;
+                v[e] = kv;
+            } else {
+                v[e] = (gi < n) ? osl * kernel_value<KID>(s) : 0.0;
+            }
+        }
+        *reinterpret_cast<double2*>(Kl + gi * ld + gj) = make_double2(v[0], v[1]);
     }
 }
 
@@ -214,6 +229,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1)
     double* aj = ai + 128;              // [128]
     double* wsum = aj + 128;            // [8][dpad+2]
     double* cta_acc = wsum + 8 * (dpad + 2);  // [dpad+2]
+    double* stage = cta_acc + (dpad + 2);     // [64][256] private per-thread slots
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -271,31 +287,39 @@ __global__ void __launch_bounds__(GR_THREADS, 1)
                     Wv[i][c] = fma(dlt, dlt, Wv[i][c]);
                 }
         }
-        double s_os = 0.0, s_tr = 0.0;
+        // The transcendental transform runs as a ROLLED loop over this thread's 32 element pairs
+        // (values parked in a private shared-memory slab, slot e at stage[e*256+tid]; no barrier:
+        // a thread only reads back what it wrote).  Fully unrolled it overflows the instruction cache.
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) stage[(i * 8 + c) * GR_THREADS + tid] = Wv[i][c];
+        double s_os = 0.0, s_tr = 0.0;
+#pragma unroll 4
+        for (int pr = 0; pr < 32; ++pr) {
+            const int i = pr >> 2, j = pr & 3;
             const long long gi = i0 + rbase + i * 8;
             const double a_i = ai[rbase + i * 8];
+            const int cl0 = cbase + j * 8;
+            const double2 kv = *reinterpret_cast<const double2*>(Kl + gi * ld + j0 + cl0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int cl0 = cbase + j * 8;
-                const double2 kv = *reinterpret_cast<const double2*>(Kl + gi * ld + j0 + cl0);
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int c = 2 * j + e;
-                    const int cl = cl0 + e;
-                    const long long gj = j0 + cl;
-                    double w = (gj < gi) ? 2.0 : (gj == gi ? 1.0 : 0.0);
-                    if (gi >= n || gj >= n) w = 0.0;
-                    const double Wij = 0.5 * (a_i * aj[cl] - (e ? kv.y : kv.x));
-                    double kk, dk;
-                    kernel_value_grad<KID>(Wv[i][c], kk, dk);
-                    s_os = fma(w * Wij, kk, s_os);
-                    if (gj == gi && gi < n) s_tr += Wij;
-                    Wv[i][c] = w * Wij * osl * dk;
-                }
+            for (int e = 0; e < 2; ++e) {
+                const int cl = cl0 + e;
+                const long long gj = j0 + cl;
+                double w = (gj < gi) ? 2.0 : (gj == gi ? 1.0 : 0.0);
+                if (gi >= n || gj >= n) w = 0.0;
+                const double Wij = 0.5 * (a_i * aj[cl] - (e ? kv.y : kv.x));
+                double kk, dk;
+                kernel_value_grad<KID>(stage[(pr * 2 + e) * GR_THREADS + tid], kk, dk);
+                s_os = fma(w * Wij, kk, s_os);
+                if (gj == gi && gi < n) s_tr += Wij;
+                stage[(pr * 2 + e) * GR_THREADS + tid] = w * Wij * osl * dk;
             }
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) Wv[i][c] = stage[(i * 8 + c) * GR_THREADS + tid];
         // per-dimension accumulation  sum A_ij (z_ik - z_jk)^2
         for (int k = 0; k < dpad; ++k) {
             double zi[8], zj[8];
@@ -413,7 +437,7 @@ int plmc_gram(const double* Z, const double* zn, int kernel_id, const double* os
     const long long tm = npad / 128;
     const long long tiles = tm * (tm + 1) / 2;
     if (tiles > 2147483647LL) return PLMC_ERR_BADARG;
-    const size_t smem = (size_t)(2 * 128 * gram_lds(dpad) + 256) * 8;
+    const size_t smem = (size_t)(2 * 128 * gram_lds(dpad < GR_KC ? dpad : GR_KC) + 256 + 64 * GR_THREADS) * 8;
     if (smem > 227 * 1024) return PLMC_ERR_BADARG;
     return launch_gram<0>(kernel_id, dim3((unsigned)tiles, 1, q), smem, (cudaStream_t)stream, Z, zn, npad, Z, zn, npad,
                           os, diag_add, K, ld, stride, n, dpad, (int)tm);
@@ -427,7 +451,7 @@ int plmc_cross_gram(const double* Ztrain, const double* zntrain, const double* Z
         return PLMC_ERR_BADARG;
     const long long tr = npad / 128, tc = mt / 128;
     if (tr * tc > 2147483647LL) return PLMC_ERR_BADARG;
-    const size_t smem = (size_t)(2 * 128 * gram_lds(dpad) + 256) * 8;
+    const size_t smem = (size_t)(2 * 128 * gram_lds(dpad < GR_KC ? dpad : GR_KC) + 256 + 64 * GR_THREADS) * 8;
     if (smem > 227 * 1024) return PLMC_ERR_BADARG;
     return launch_gram<1>(kernel_id, dim3((unsigned)(tr * tc), 1, q), smem, (cudaStream_t)stream, Ztrain, zntrain,
                           npad, Ztest, zntest, mt_rows_pad, os, nullptr, Kx, ldx, stride, n, dpad, (int)tc);
@@ -453,7 +477,7 @@ int plmc_grad_sweep(const double* Kinv, long long ld, long long stride, const do
     const long long tm = npad / 128;
     const long long ntiles = tm * (tm + 1) / 2;
     const int ctas = sweep_ctas(ntiles);
-    const size_t smem = (size_t)(2 * 128 * (dpad + 1) + 256 + 9 * (dpad + 2)) * 8;
+    const size_t smem = (size_t)(2 * 128 * (dpad + 1) + 256 + 9 * (dpad + 2) + 64 * GR_THREADS) * 8;
     if (smem > 227 * 1024) return PLMC_ERR_BADARG;
     dim3 grid(ctas, 1, q);
 #define PLMC_SWEEP_CASE(KID)                                                                                     \

@@ -74,3 +74,47 @@ int plmc_peak_copy(const double* src, double* dst, long long n, void* stream) {
     return PLMC_OK;
 }
 }
+
+// ---- do DMMA (tensor pipe) and DFMA (FP64 pipe) overlap? ---------------------------------
+// even warps run the DMMA loop, odd warps the DFMA loop, in the same CTA.
+namespace plmc {
+__global__ void __launch_bounds__(1024) peak_mixed_kernel(double* out, long long iters_mma, long long iters_fma,
+                                                          double seed) {
+    const int warp = threadIdx.x >> 5;
+    double s = 0.0;
+    if ((warp & 1) == 0) {
+        double c[8][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+        double a = seed + threadIdx.x * 1e-9, b = seed * 0.5;
+        for (long long it = 0; it < iters_mma; ++it) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dmma884(c[i][0], c[i][1], a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+    } else {
+        double c[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) c[i] = i * 1e-3;
+        const double a = 1.0 + seed * 1e-12, b = seed * 1e-9 + threadIdx.x * 1e-12;
+        for (long long it = 0; it < iters_fma; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) c[i] = fma(c[i], a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += c[i];
+    }
+    if (s == 123.456) out[0] = s;
+}
+}  // namespace plmc
+
+extern "C" int plmc_peak_mixed(int blocks, int threads, long long iters_mma, long long iters_fma, double* scratch,
+                               void* stream) {
+    if (blocks <= 0 || threads <= 0 || threads > 1024 || (threads & 63)) return PLMC_ERR_BADARG;
+    plmc::peak_mixed_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(scratch, iters_mma, iters_fma, 1.0);
+    PLMC_CHECK_LAUNCH();
+    return PLMC_OK;
+}
