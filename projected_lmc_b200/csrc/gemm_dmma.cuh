@@ -60,6 +60,41 @@ __device__ __forceinline__ void cp_async16s(uint32_t smem_addr, const void* gmem
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr), "l"(gmem_src), "r"(src_bytes));
 }
 
+// Alternative pipeline synchronisation (per-stage mbarriers instead of one CTA barrier per
+// k-tile).  Validated on B200 but not faster (33.8 vs 34.2 TFLOP/s at 8192^3): the CTA
+// barrier is not what limits the kernel, so the simpler scheme stays the default.
+#ifndef PLMC_GEMM_MBAR
+#define PLMC_GEMM_MBAR 0
+#endif
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+// arrive on `bar` once all cp.async copies previously issued by this thread have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
 // Per-thread copy plan for one operand: G_NCH chunks per k-tile.
 //   KC: element (x, k) at P[(x0+x)*ld + k],  chunk c -> row c / (G_BK/2), col-pair c % (G_BK/2)
 //   MC: element (x, k) at P[k*ld + x0+x],    chunk c -> k-row c / 64,     col-pair c % 64
@@ -173,6 +208,59 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(const GemmArgs 
         lb.load(sb + G_TILE * 8u, kt);
     };
 
+#if PLMC_GEMM_MBAR
+    // Split arrive/wait pipeline: per-stage "full" mbarriers are completed by the cp.async
+    // copies of all 256 threads, per-stage "empty" mbarriers by the 8 consumer warps.  No
+    // CTA-wide barrier in the loop: a warp only ever waits for data, or (mid-tile, when it
+    // refills a stage) for the other warps to have finished the PREVIOUS tile.
+    __shared__ __align__(8) unsigned long long full_bar[G_STAGES];
+    __shared__ __align__(8) unsigned long long empty_bar[G_STAGES];
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < G_STAGES; ++s) {
+            mbar_init(&full_bar[s], G_THREADS);
+            mbar_init(&empty_bar[s], G_THREADS / 32);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < G_STAGES - 1; ++s) {
+        if (s < nk) {
+            issue(s);
+            cp_async_mbar_arrive(&full_bar[s]);
+        }
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        mbar_wait(&full_bar[kt % G_STAGES], (kt / G_STAGES) & 1);
+        const double* sa = smem + (kt % G_STAGES) * G_STAGE;
+        const double* sb = sa + G_TILE;
+        const double* pa = A_KC ? sa + (wm * 64 + g) * G_LDK + t : sa + t * G_LDM + wm * 64 + g;
+        const double* pb = B_KC ? sb + (wn * 32 + g) * G_LDK + t : sb + t * G_LDM + wn * 32 + g;
+        const int nt = kt + G_STAGES - 1;
+#pragma unroll
+        for (int kk = 0; kk < G_BK / 4; ++kk) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) af[i] = A_KC ? pa[i * 8 * G_LDK + kk * 4] : pa[kk * 4 * G_LDM + i * 8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = B_KC ? pb[j * 8 * G_LDK + kk * 4] : pb[kk * 4 * G_LDM + j * 8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            if (kk == (wm ? G_BK / 8 : 0)) {
+                if (nt < nk) {
+                    const int rn = nt / G_STAGES;
+                    if (rn > 0) mbar_wait(&empty_bar[nt % G_STAGES], (rn - 1) & 1);
+                    issue(nt);
+                    cp_async_mbar_arrive(&full_bar[nt % G_STAGES]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[kt % G_STAGES]);
+    }
+#else
     // ---- prologue ---------------------------------------------------------
 #pragma unroll
     for (int s = 0; s < G_STAGES - 1; ++s) {
@@ -209,6 +297,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(const GemmArgs 
         }
     }
     cp_async_wait<0>();
+#endif
 
     // ---- epilogue ---------------------------------------------------------
     const double alpha = p.alpha, beta = p.beta;
