@@ -98,9 +98,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples that arrived inside the timed window [t0, t1] (host clock)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -110,7 +111,13 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = [(ts, ln) for ts, ln in self.lines if t0 is None or (t0 <= ts <= t1)]
+        window = "timed region"
+        if not lines and self.lines and t0 is not None:  # region shorter than the 200 ms sampling period
+            mid = 0.5 * (t0 + t1)
+            lines = sorted(self.lines, key=lambda x: abs(x[0] - mid))[:3]
+            window = "nearest samples (timed region shorter than the sampling period)"
+        for _, ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -123,7 +130,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 def measured_peaks():
@@ -255,15 +262,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     peak = dmma_peak_tflops()
 
     # ---- timed region: device-resident inputs --------------------------------------
     eng = model._engine
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    t_wall0 = time.time()
     eng.profile = []
     ops.stats_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -272,7 +280,7 @@ def main():
         loss = step()
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, time.time())
     launches, gemm_launches, gemm_flops = ops.stats_get()
     phases = eng.phase_ms()
     eng.profile = None

@@ -10,10 +10,11 @@ from .mixing import (LMCMixingMatrix, LowerTriangularParam, PositiveDiagonalPara
                      UpperTriangularParam)
 from .mll import ProjectedLMCmll, projection_terms  # noqa: F401
 from .models import ExactGPModel, ProjectedGPModel, handle_covar_, init_lmc_coefficients  # noqa: F401
+from .training import fit  # noqa: F401
 
 __version__ = "0.1.0"
 __all__ = [
     "gp", "ProjectedGPModel", "ProjectedLMCmll", "ExactGPModel", "LMCMixingMatrix", "ScalarParam",
     "PositiveDiagonalParam", "UpperTriangularParam", "LowerTriangularParam", "handle_covar_",
-    "init_lmc_coefficients", "LatentEngine", "NotPSDError", "projection_terms",
+    "init_lmc_coefficients", "LatentEngine", "NotPSDError", "projection_terms", "fit",
 ]

@@ -77,6 +77,7 @@ class LatentEngine:
             return
         base = settings.cholesky_jitter.value()
         prev_bad = bad
+        new = 0.0
         for i in range(max_tries):
             new = base * (10**i)
             warnings.warn(f"A not p.d., added jitter of {new:.1e} to the diagonal", RuntimeWarning)
@@ -143,6 +144,17 @@ class LatentEngine:
                 out[name] = out.get(name, 0.0) + prev.elapsed_time(ev)
             prev = ev
         return out
+
+    # -- dense noisy train covariance (kernel_cond, projected_lmc.py:367-369; small n only) --------
+    def dense_gram(self, X, ell, os_, noise, kid):
+        n, d = X.shape
+        q = ell.shape[0]
+        ws = self.workspace(X.device, q, n)
+        np_ = ws["K"].shape[1]
+        Z, zn = ops.scale_inputs(X, self.xmean(X), ell, np_)
+        ops.gram(Z, zn, kid, os_, noise, ws["K"], n)
+        K = ws["K"][:, :n, :n]
+        return torch.tril(K) + torch.tril(K, -1).transpose(1, 2)
 
     # -- leave-one-out by-product (projected_lmc.py:1108-1119) ----------------------
     def loo(self, X, TY, ell, os_, noise, kid, max_tries=None):

@@ -344,6 +344,16 @@ class ProjectedGPModel(ExactGPModel):
             m, v = self._engine.predict_latents(st, xs)
         return LatentPosterior(m.to(x.dtype), v.to(x.dtype))
 
+    def kernel_cond(self):
+        """Condition numbers of the noisy latent train covariances K_l + s_l I (dense SVD: small n)."""
+        with torch.no_grad():
+            X = _as_f64(self.train_inputs[0])
+            kid, ell, os_, noise = self._kernel_params()
+            K = self._engine.dense_gram(X, _as_f64(ell).contiguous(),
+                                        None if os_ is None else _as_f64(os_).contiguous(),
+                                        _as_f64(noise).contiguous(), kid)
+            return torch.linalg.cond(K)
+
     def compute_loo(self, output=None):
         """Leave-one-out predictive variances and residuals of the latent GPs,
         both n_points x n_latents (by-product of K^-1 and alpha)."""

@@ -159,3 +159,97 @@ def test_loo_matches_dense():
         s2_ref = 1.0 / torch.diagonal(Kinv, dim1=1, dim2=2)
         r_ref = (Kinv @ TY.unsqueeze(-1)).squeeze(-1) * s2_ref
     assert rel_err(s2, s2_ref.T) < 1e-8 and rel_err(r, r_ref.T) < 1e-8
+
+
+def test_kernel_cond_matches_dense():
+    X, Y, _, _ = synth(90, 3, 5, 2)
+    m = make_model(X, Y, 2, variant="PLMC", kernel="rbf")
+    mc = cpu_copy(m)
+    m = m.cuda()
+    op = oracle_params(mc)
+    with torch.no_grad():
+        K = O.gram(op, X, training=False) + torch.diag_embed(O.noise(op)[:, None].expand(-1, 90))
+        ref = torch.linalg.cond(K)
+    assert rel_err(m.kernel_cond(), ref) < 1e-8
+
+
+def test_fit_loop_matches_oracle_adamw_trajectory():
+    """The reference's training loop (AdamW + exponential LR decay, experiments.py:259-284): the CUDA
+    path and the CPU oracle must produce the same loss trajectory."""
+    from projected_lmc_b200 import fit
+
+    X, Y, _, _ = synth(120, 2, 5, 2, seed=8)
+    m = make_model(X, Y, 2, variant="PLMC", kernel="matern52")
+    mc = cpu_copy(m)
+    m = m.cuda()
+    n_iter, lr, lr_min = 12, 1e-2, 1e-3
+    out = fit(m, ProjectedLMCmll(m.likelihood, m), X.cuda(), Y.cuda(), n_iter=n_iter, lr=lr, lr_min=lr_min,
+              check_every=5, patience=500)
+    assert out["n_iter"] == n_iter and out["stopped_at"] is None
+    opt = torch.optim.AdamW(mc.parameters(), lr=lr)
+    sch = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=float(torch.tensor(lr_min / lr).log().div(n_iter).exp()))
+    ref = []
+    mc.train()
+    for _ in range(n_iter):
+        opt.zero_grad()
+        loss = -O.mll(oracle_params(mc), X, Y)
+        loss.backward()
+        opt.step()
+        sch.step()
+        ref.append(loss.item())
+    assert rel_err(out["losses"], torch.tensor(ref)) < 1e-7
+    assert out["losses"][-1] < out["losses"][0]
+
+
+def test_fit_plateau_stop_rule():
+    from projected_lmc_b200 import fit
+
+    X, Y, _, _ = synth(64, 2, 4, 2, seed=2)
+    m = make_model(X, Y, 2, variant="PLMC_fast", kernel="rbf").cuda()
+    out = fit(m, ProjectedLMCmll(m.likelihood, m), X.cuda(), Y.cuda(), n_iter=60, lr=1e-6, lr_min=None,
+              loss_thresh=1e-2, patience=7, check_every=4)
+    # with a vanishing learning rate every step is a plateau step: the rule fires at iteration patience + 1
+    assert out["stopped_at"] == 8 and out["n_iter"] <= 12
+
+
+def test_eval_cache_is_invalidated_by_parameter_updates():
+    X, Y, Xs, _ = synth(100, 2, 5, 2, ns=20)
+    m = make_model(X, Y, 2, variant="PLMC", kernel="rbf").cuda()
+    m.eval()
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = m(Xs.cuda()).mean.clone()
+        b = m(Xs.cuda()).mean.clone()
+        assert torch.equal(a, b)
+        key = m._pred_key
+        m.covar_module.raw_lengthscale.add_(0.3)
+        c = m(Xs.cuda()).mean
+        assert m._pred_key != key and not torch.allclose(a, c)
+
+
+def test_float32_inputs_are_computed_in_float64():
+    X, Y, Xs, _ = synth(80, 2, 4, 2, ns=10)
+    m = make_model(X, Y, 2, variant="PLMC_fast", kernel="rbf")
+    ref = -O.mll(oracle_params(cpu_copy(m)), X, Y)
+    m32 = m.float().cuda()
+    loss = -ProjectedLMCmll(m32.likelihood, m32)(m32(X.float().cuda()), Y.float().cuda())
+    assert loss.dtype == torch.float32
+    assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())       # north_star fp32 tolerance
+    loss.backward()
+    assert all(p.grad is not None and p.grad.dtype == torch.float32 for p in m32.parameters())
+
+
+def test_not_psd_error_after_max_tries():
+    from projected_lmc_b200 import NotPSDError
+
+    X, Y, _, _ = synth(100, 2, 4, 2)
+    X[50:] = X[:50]                       # exactly duplicated points, no noise to speak of -> singular
+    m = make_model(X, Y, 2, variant="PLMC_fast", kernel="rbf", perturb=False, noise_thresh=-60.0)
+    with torch.no_grad():
+        m.likelihood.noise_covar.raw_noise.fill_(-80.0)
+    m = m.cuda()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # a jitter far below the rounding level cannot repair the singular matrix
+        with gp.settings.cholesky_max_tries(2), gp.settings.cholesky_jitter(1e-40), pytest.raises(NotPSDError):
+            ProjectedLMCmll(m.likelihood, m)(m(X.cuda()), Y.cuda())
