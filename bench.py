@@ -34,7 +34,9 @@ WORKLOADS = {
     # name: (n, d, tasks/gpu, latents/gpu, kernel, variant)
     "c2": dict(n=44484, d=21, p=7, q=4, kernel="matern52", label="C2 SARCOS-shaped projected LMC"),
     "c1": dict(n=1000, d=6, p=50, q=10, kernel="rbf", label="C1 experiments.py-style projected LMC"),
-    "c4": dict(n=20000, d=8, p=500, q=32, kernel="rbf", label="C4 many-task projected LMC"),
+    # C4 / C5 are quoted on 8 GPUs (500 tasks / 32 latents, 20 tasks / 8 latents): per-GPU shares below
+    "c4": dict(n=20000, d=8, p=63, q=4, kernel="rbf", label="C4 many-task projected LMC (4 latents, 63 tasks per GPU)"),
+    "c5": dict(n=100000, d=4, p=3, q=1, kernel="rbf", label="C5 large-n projected LMC (1 latent, 3 tasks per GPU)"),
 }
 CPU_SAMPLE_N = 2000
 
