@@ -135,6 +135,16 @@ int plmc_gemm(int layout, const double* A, long long lda, long long sA, const do
               double* C, long long ldc, long long sC, int M, int N, int K, double alpha, double beta, int lower,
               int triA, int triB, int batch, void* stream);
 
+/* ---- FP64 GEMM on the tcgen05 INT8 tensor path (Ozaki splitting; csrc/ozaki.cu):
+ * C = alpha op(A) op(B) + beta C for ONE matrix, beta in {0,1}, M%128==0, N%64==0, K%32==0.
+ * `slices` (1..7) signed 8-bit planes of 7 bits per operand -> 7*slices mantissa bits relative
+ * to the largest entry of each row of op(A) / column of op(B).  same_operand != 0: op(B)^T is
+ * op(A) (SYRK), sliced once.  ws: plmc_ozaki_ws_bytes(...) bytes of scratch.                  */
+long long plmc_ozaki_ws_bytes(int M, int N, int K, int slices, int same_operand);
+int plmc_ozaki_gemm(int layout, const double* A, long long lda, const double* B, long long ldb, double* C,
+                    long long ldc, int M, int N, int K, double alpha, double beta, int lower, int slices,
+                    int same_operand, void* ws, long long ws_bytes, void* stream);
+
 /* ---- roofline denominators (time with CUDA events on `stream`) */
 int plmc_peak_dmma(int blocks, int threads, long long iters, double* scratch, void* stream);
 int plmc_peak_dfma(int blocks, int threads, long long iters, double* scratch, void* stream);

@@ -47,12 +47,14 @@ _SIGNATURES = {
     "plmc_latent_var": [P, LL, LL, P, P, LL, LL, LL, I, P],
     "plmc_mix_tasks": [P, P, LL, P, P, P, P, LL, I, I, I, P],
     "plmc_gemm": [I, P, LL, LL, P, LL, LL, P, LL, LL, I, I, I, D, D, I, I, I, I, P],
+    "plmc_ozaki_ws_bytes": [I, I, I, I, I],
+    "plmc_ozaki_gemm": [I, P, LL, P, LL, P, LL, I, I, I, D, D, I, I, I, P, LL, P],
     "plmc_peak_dmma": [I, I, LL, P, P],
     "plmc_peak_dfma": [I, I, LL, P, P],
     "plmc_peak_copy": [P, P, LL, P],
     "plmc_peak_mixed": [I, I, LL, LL, P, P],
 }
-_RET_LL = {"plmc_npad", "plmc_dinv_bytes", "plmc_project_bwd_ws", "plmc_grad_ws", "plmc_trmv_ws"}
+_RET_LL = {"plmc_npad", "plmc_dinv_bytes", "plmc_project_bwd_ws", "plmc_grad_ws", "plmc_trmv_ws", "plmc_ozaki_ws_bytes"}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -110,7 +112,7 @@ def ptr(t) -> c_void_p:
         return c_void_p(0)
     if not t.is_cuda:
         raise PlmcError("libplmc_b200 was handed a non-CUDA tensor; there is no CPU fallback")
-    if t.dtype not in (torch.float64, torch.int32):
+    if t.dtype not in (torch.float64, torch.int32, torch.uint8):
         raise PlmcError(f"libplmc_b200 works on float64 / int32 buffers, got {t.dtype}")
     return c_void_p(t.data_ptr())
 

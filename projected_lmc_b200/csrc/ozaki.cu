@@ -1,0 +1,448 @@
+// FP64 GEMM through the 5th-generation tensor cores (tcgen05 / TMEM / TMA):
+// Ozaki-style error-free slicing of the FP64 operands into signed 8-bit planes,
+// exact INT8 x INT8 -> INT32 products on tcgen05.mma.kind::i8, FP64 recombination.
+//
+// Why: B200 has no FP64 kind on tcgen05 and its DMMA/DFMA datapath tops out at
+// 37 TFLOP/s (measured; the two share one unit, see plmc_peak_mixed).  The INT8
+// tensor path is two orders of magnitude wider, so a product of two FP64 matrices
+// split into s planes of 7 bits costs s(s+1)/2 INT8 GEMMs and still wins.
+//
+//   x = A[m,k] * 2^-ea[m]  (|x| < 1),  a_i = trunc(x * 2^7), x <- x * 2^7 - a_i   (i < s, exact)
+//   A[m,k] = 2^ea[m] * sum_i a_i 2^-7(i+1) + O(2^-7s)        (same for columns of B)
+//   C[m,n] += alpha * 2^(ea[m]+eb[n]-14) * sum_{g<s} 2^-7g * D_g[m,n],
+//   D_g = sum_{i+j=g} A_i B_j^T   (INT32, exact for K-chunks <= 16384)
+//
+// Kernel: one CTA per 128 x 64 output tile; all s A-planes and s B-planes of a
+// 32-byte K-step are staged by TMA (SWIZZLE_32B) in a 5-stage mbarrier ring, one
+// elected thread issues the s(s+1)/2 MMAs per stage into s TMEM accumulators
+// (one per diagonal g, 64 columns each), four epilogue warps read TMEM back
+// (tcgen05.ld), recombine in FP64 and update C in place.
+#include <cuda.h>
+
+#include "plmc_common.cuh"
+
+namespace plmc {
+
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 32;   // BK in int8 elements = bytes
+constexpr int OZ_SMAX = 7;                           // TMEM: 7 accumulators x 64 columns = 448 <= 512
+constexpr int OZ_STAGES = 5;
+constexpr int OZ_THREADS = 192;                      // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int OZ_KCHUNK = 16384;                     // INT32 exactness: 7 * 16384 * 127^2 < 2^31
+constexpr int OZ_A_PLANE = OZ_BM * OZ_BK;            // 4096 B
+constexpr int OZ_B_PLANE = OZ_BN * OZ_BK;            // 2048 B
+
+__host__ __device__ inline int oz_stage_bytes(int s) { return s * (OZ_A_PLANE + OZ_B_PLANE); }
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init_(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// K-major, SWIZZLE_32B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_32B=6 [61,64)
+// rows are 32 B apart, 8-row groups 256 B apart (SBO); LBO is unused for swizzled K-major (1).
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)6 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::i8, S32 accumulate, K-major A and B
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+struct OzArgs {
+    double* C;
+    long long ldc;
+    const int* ea;  // [M] row exponents of op(A)
+    const int* eb;  // [N] column exponents of op(B)
+    int M, N, K;    // K % 32 == 0
+    int s;          // planes (1..7)
+    double alpha;
+    int beta_one;   // 1: C += ..., 0: C = ...
+    int lower;      // skip tiles entirely above the diagonal (C origin on the diagonal)
+};
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+    ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                      const OzArgs p) {
+    extern __shared__ __align__(1024) uint8_t oz_smem[];
+    __shared__ __align__(8) unsigned long long full_bar[OZ_STAGES], empty_bar[OZ_STAGES], acc_full, acc_empty;
+    __shared__ uint32_t tmem_base_sh;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * OZ_BM, n0 = blockIdx.x * OZ_BN;
+    if (p.lower && n0 > m0 + OZ_BM - 1) return;   // whole CTA exits before any barrier / allocation
+
+    const int s = p.s;
+    const int stage_bytes = oz_stage_bytes(s);
+    const uint32_t smem0 = (smem_u32(oz_smem) + 1023u) & ~1023u;
+    const int nkt = p.K / OZ_BK;
+    const int kt_per_chunk = OZ_KCHUNK / OZ_BK;
+    const int nchunks = (nkt + kt_per_chunk - 1) / kt_per_chunk;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < OZ_STAGES; ++i) {
+            mbar_init_(smem_u32(&full_bar[i]), 1);
+            mbar_init_(smem_u32(&empty_bar[i]), 1);
+        }
+        mbar_init_(smem_u32(&acc_full), 1);
+        mbar_init_(smem_u32(&acc_empty), 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_sh))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            for (int kt = 0; kt < nkt; ++kt) {
+                const int st = kt % OZ_STAGES, round = kt / OZ_STAGES;
+                if (round > 0) mbar_wait_(smem_u32(&empty_bar[st]), (round - 1) & 1);
+                const uint32_t fb = smem_u32(&full_bar[st]);
+                mbar_expect_tx_(fb, (uint32_t)stage_bytes);
+                const uint32_t sa = smem0 + (uint32_t)st * stage_bytes;
+                const uint32_t sb = sa + (uint32_t)s * OZ_A_PLANE;
+                for (int i = 0; i < s; ++i) tma_load_3d(sa + i * OZ_A_PLANE, &mapA, fb, kt * OZ_BK, m0, i);
+                for (int j = 0; j < s; ++j) tma_load_3d(sb + j * OZ_B_PLANE, &mapB, fb, kt * OZ_BK, n0, j);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = umma_idesc_i8(OZ_BM, OZ_BN);
+        for (int ch = 0; ch < nchunks; ++ch) {
+            if (ch > 0) {   // accumulators must have been drained by the epilogue warps
+                mbar_wait_(smem_u32(&acc_empty), (ch - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            const int kt0 = ch * kt_per_chunk, kt1 = min(nkt, kt0 + kt_per_chunk);
+            for (int kt = kt0; kt < kt1; ++kt) {
+                const int st = kt % OZ_STAGES, round = kt / OZ_STAGES;
+                mbar_wait_(smem_u32(&full_bar[st]), round & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint32_t sa = smem0 + (uint32_t)st * stage_bytes;
+                    const uint32_t sb = sa + (uint32_t)s * OZ_A_PLANE;
+                    for (int i = 0; i < s; ++i) {
+                        const uint64_t da = umma_desc_sw32(sa + i * OZ_A_PLANE);
+                        for (int j = 0; i + j < s; ++j) {
+                            const uint64_t db = umma_desc_sw32(sb + j * OZ_B_PLANE);
+                            // accumulator of diagonal g = i + j; first write of the chunk: pair (0, g) at kt0
+                            umma_i8(tmem_base + (uint32_t)(i + j) * OZ_BN, da, db, idesc, (kt > kt0 || i > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(smem_u32(&empty_bar[st]));            // frees the smem stage when the MMAs retire
+                    if (kt == kt1 - 1) umma_commit(smem_u32(&acc_full));  // accumulators complete for this chunk
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> FP64 recombination -> C =====
+        const int quad = warp & 3;                 // TMEM lane quarter this warp may access
+        const int row = m0 + quad * 32 + lane;
+        const double sa = scalbn(1.0, p.ea[row] - 14);
+        double* crow = p.C + (long long)row * p.ldc + n0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            mbar_wait_(smem_u32(&acc_full), ch & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const bool add = p.beta_one || ch > 0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+                double v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.0;
+                for (int gI = s - 1; gI >= 0; --gI) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(gI * OZ_BN + c0), r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fma(v[j], 0.0078125, (double)(int)r[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const int col = n0 + c0 + j;
+                    const double f0 = scalbn(sa, p.eb[col]), f1 = scalbn(sa, p.eb[col + 1]);
+                    double2 out = make_double2(p.alpha * f0 * v[j], p.alpha * f1 * v[j + 1]);
+                    double2* dst = reinterpret_cast<double2*>(crow + c0 + j);
+                    if (add) {
+                        const double2 old = *dst;
+                        out.x += old.x;
+                        out.y += old.y;
+                    }
+                    *dst = out;
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_(smem_u32(&acc_empty));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// slicing: FP64 -> s signed 8-bit planes, K-contiguous, with per-row power-of-two scaling
+//   KC operand: element (x, k) at P[x*ld + k]   ;   MC operand: element (x, k) at P[k*ld + x]
+// planes[i][x][k] (x < X, k < K),  ex[x] = exponent with |P(x,:)| * 2^-ex < 1
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int exp_for(double amax) {
+    if (!(amax > 0.0)) return 0;
+    int e;
+    frexp(amax, &e);     // amax = f * 2^e, f in [0.5, 1)  ->  amax * 2^-e < 1
+    return e;
+}
+
+// one CTA per row (KC): coalesced along k
+__global__ void __launch_bounds__(256) slice_kc_kernel(const double* __restrict__ P, long long ld, int X, int K,
+                                                       int s, int8_t* __restrict__ planes, int* __restrict__ ex) {
+    __shared__ double red[8];
+    __shared__ int e_sh;
+    const int x = blockIdx.x;
+    const double* row = P + (long long)x * ld;
+    double amax = 0.0;
+    for (int k = threadIdx.x; k < K; k += 256) amax = fmax(amax, fabs(row[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = red[0];
+        for (int w = 1; w < 8; ++w) m = fmax(m, red[w]);
+        e_sh = exp_for(m);
+        ex[x] = e_sh;
+    }
+    __syncthreads();
+    const int e = e_sh;
+    const long long plane_stride = (long long)X * K;
+    // 4 consecutive k per thread -> one 32-bit store per plane
+    for (int k4 = threadIdx.x * 4; k4 < K; k4 += 1024) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = scalbn(row[k4 + u], -e);
+        for (int i = 0; i < s; ++i) {
+            uint32_t pack = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double t = v[u] * 128.0;
+                const double a = trunc(t);
+                v[u] = t - a;
+                pack |= ((uint32_t)(uint8_t)(int8_t)(int)a) << (8 * u);
+            }
+            *reinterpret_cast<uint32_t*>(planes + i * plane_stride + (long long)x * K + k4) = pack;
+        }
+    }
+}
+
+// MC operand, pass 1: column-wise absmax over k   (threads along x: coalesced)
+__global__ void __launch_bounds__(256) absmax_mc_kernel(const double* __restrict__ P, long long ld, int X, int K,
+                                                        int* __restrict__ ex) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    if (x >= X) return;
+    double amax = 0.0;
+    for (int k = 0; k < K; ++k) amax = fmax(amax, fabs(P[(long long)k * ld + x]));
+    ex[x] = exp_for(amax);
+}
+
+// MC operand, pass 2: 32(k) x 32(x) tiles transposed through shared memory
+__global__ void __launch_bounds__(256) slice_mc_kernel(const double* __restrict__ P, long long ld, int X, int K,
+                                                       int s, int8_t* __restrict__ planes,
+                                                       const int* __restrict__ ex) {
+    __shared__ double tile[32][33];
+    const int x0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows of 32
+    for (int r = ty; r < 32; r += 8) tile[r][tx] = P[(long long)(k0 + r) * ld + x0 + tx];   // tile[k][x]
+    __syncthreads();
+    // thread -> (x = threadIdx.x / 8, 4 consecutive k = (threadIdx.x % 8) * 4)
+    const int xl = threadIdx.x >> 3, kl = (threadIdx.x & 7) * 4;
+    const int e = ex[x0 + xl];
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = scalbn(tile[kl + u][xl], -e);
+    const long long plane_stride = (long long)X * K;
+    for (int i = 0; i < s; ++i) {
+        uint32_t pack = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double t = v[u] * 128.0;
+            const double a = trunc(t);
+            v[u] = t - a;
+            pack |= ((uint32_t)(uint8_t)(int8_t)(int)a) << (8 * u);
+        }
+        *reinterpret_cast<uint32_t*>(planes + i * plane_stride + (long long)(x0 + xl) * K + k0 + kl) = pack;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encode() {
+    if (g_encode) return PLMC_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+        return PLMC_ERR_LAUNCH;
+    g_encode = (EncodeTiledFn)fn;
+    return PLMC_OK;
+}
+
+// planes [s][X][K] int8 -> 3-D map, box {32 B, box_rows, 1}, SWIZZLE_32B
+static int make_plane_map(CUtensorMap* map, const int8_t* planes, int X, int K, int s, int box_rows) {
+    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)X, (cuuint64_t)s};
+    const cuuint64_t strides[2] = {(cuuint64_t)K, (cuuint64_t)K * (cuuint64_t)X};
+    const cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PLMC_OK : PLMC_ERR_LAUNCH;
+}
+
+static bool g_oz_attr = false;
+
+long long ozaki_ws_bytes(int M, int N, int K, int s, bool same_operand) {
+    const long long a = (long long)s * M * K, b = same_operand ? 0 : (long long)s * N * K;
+    const long long pad = 1024;
+    return ((a + pad - 1) / pad) * pad + ((b + pad - 1) / pad) * pad + 4LL * (M + N) + 2 * pad;
+}
+
+// C = alpha * op(A) op(B) + beta * C   (beta in {0, 1}),  one batch member.
+// aKC / bKC as in gemm_dmma (bKC: B(k,n) at B[n*ldb+k]).  same_operand: op(B)^T == op(A) (SYRK).
+int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, const double* B, long long ldb, double* C,
+               long long ldc, int M, int N, int K, double alpha, double beta, int lower, int s, bool same_operand,
+               void* ws, long long ws_bytes, cudaStream_t st) {
+    if (s < 1 || s > OZ_SMAX || (M % OZ_BM) || (N % OZ_BN) || (K % 32) || (beta != 0.0 && beta != 1.0))
+        return PLMC_ERR_BADARG;
+    if (same_operand && (M != N)) return PLMC_ERR_BADARG;
+    if (ws_bytes < ozaki_ws_bytes(M, N, K, s, same_operand)) return PLMC_ERR_BADARG;
+    if (get_encode()) return PLMC_ERR_LAUNCH;
+    const long long pad = 1024;
+    uint8_t* w = (uint8_t*)ws;
+    w = (uint8_t*)(((uintptr_t)w + pad - 1) / pad * pad);
+    int8_t* pa = (int8_t*)w;
+    w += (((long long)s * M * K + pad - 1) / pad) * pad;
+    int8_t* pb = same_operand ? pa : (int8_t*)w;
+    if (!same_operand) w += (((long long)s * N * K + pad - 1) / pad) * pad;
+    int* ea = (int*)w;
+    int* eb = same_operand ? ea : ea + M;
+
+    auto slice = [&](bool kc, const double* P, long long ld, int X, int8_t* planes, int* ex) {
+        if (kc) {
+            slice_kc_kernel<<<X, 256, 0, st>>>(P, ld, X, K, s, planes, ex);
+        } else {
+            absmax_mc_kernel<<<(X + 255) / 256, 256, 0, st>>>(P, ld, X, K, ex);
+            slice_mc_kernel<<<dim3(X / 32, K / 32), 256, 0, st>>>(P, ld, X, K, s, planes, ex);
+        }
+    };
+    slice(aKC, A, lda, M, pa, ea);
+    if (!same_operand) slice(bKC, B, ldb, N, pb, eb);
+    PLMC_CHECK_LAUNCH();
+
+    CUtensorMap mapA, mapB;
+    if (make_plane_map(&mapA, pa, M, K, s, OZ_BM) || make_plane_map(&mapB, pb, N, K, s, OZ_BN)) return PLMC_ERR_LAUNCH;
+    const int smem = OZ_STAGES * oz_stage_bytes(s) + 1024;
+    if (!g_oz_attr) {
+        if (cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 OZ_STAGES * oz_stage_bytes(OZ_SMAX) + 1024) != cudaSuccess)
+            return PLMC_ERR_LAUNCH;
+        g_oz_attr = true;
+    }
+    OzArgs p;
+    p.C = C; p.ldc = ldc; p.ea = ea; p.eb = eb;
+    p.M = M; p.N = N; p.K = K; p.s = s;
+    p.alpha = alpha; p.beta_one = (beta == 1.0); p.lower = lower;
+    ozaki_gemm_kernel<<<dim3(N / OZ_BN, M / OZ_BM), OZ_THREADS, smem, st>>>(mapA, mapB, p);
+    PLMC_CHECK_LAUNCH();
+    note_launch(3);
+    return PLMC_OK;
+}
+
+}  // namespace plmc
+
+extern "C" {
+
+long long plmc_ozaki_ws_bytes(int M, int N, int K, int slices, int same_operand) {
+    return plmc::ozaki_ws_bytes(M, N, K, slices, same_operand != 0);
+}
+
+int plmc_ozaki_gemm(int layout, const double* A, long long lda, const double* B, long long ldb, double* C,
+                    long long ldc, int M, int N, int K, double alpha, double beta, int lower, int slices,
+                    int same_operand, void* ws, long long ws_bytes, void* stream) {
+    if (!A || !B || !C || !ws) return PLMC_ERR_BADARG;
+    const bool aKC = !(layout & 2), bKC = !(layout & 1);
+    return plmc::ozaki_gemm(aKC, bKC, A, lda, B, ldb, C, ldc, M, N, K, alpha, beta, lower, slices, same_operand != 0,
+                            ws, ws_bytes, (cudaStream_t)stream);
+}
+}

@@ -235,3 +235,17 @@ def stats_get():
     a, b, c = ctypes.c_longlong(0), ctypes.c_longlong(0), ctypes.c_double(0.0)
     check(_cabi.load().plmc_stats_get(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "stats_get")
     return a.value, b.value, c.value
+
+
+def ozaki_gemm(layout, A, B, C, M, N, K, alpha=1.0, beta=0.0, lower=False, slices=7, same_operand=False, ws=None):
+    """C = alpha op(A) op(B) + beta C (2-D views) on the tcgen05 INT8 path; beta in {0, 1}."""
+    need = lib().plmc_ozaki_ws_bytes(M, N, K, slices, int(same_operand))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty((need,), dtype=torch.uint8, device=C.device)
+    check(
+        lib().plmc_ozaki_gemm(layout, ptr(A), A.stride(-2), ptr(B), B.stride(-2), ptr(C), C.stride(-2), M, N, K,
+                              float(alpha), float(beta), int(lower), slices, int(same_operand), ptr(ws), ws.numel(),
+                              stream()),
+        "ozaki_gemm",
+    )
+    return C
