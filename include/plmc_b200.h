@@ -141,6 +141,11 @@ int plmc_gemm(int layout, const double* A, long long lda, long long sA, const do
  * to the largest entry of each row of op(A) / column of op(B).  same_operand != 0: op(B)^T is
  * op(A) (SYRK), sliced once.  ws: plmc_ozaki_ws_bytes(...) bytes of scratch.                  */
 long long plmc_ozaki_ws_bytes(int M, int N, int K, int slices, int same_operand);
+/* Route every GEMM of the blocked factorisation layer (potrf / trsm / trtri / lauum) whose M, N
+ * and K are all >= min_dim through the INT8 path with `slices` planes, using the caller-owned
+ * scratch `ws` (a GEMM whose planes do not fit falls back to the DMMA kernel).  slices = 0
+ * switches the emulation off (pure FP64 DMMA arithmetic).  Process-wide setting.              */
+int plmc_set_fp64_emulation(void* ws, long long ws_bytes, int slices, int min_dim);
 int plmc_ozaki_gemm(int layout, const double* A, long long lda, const double* B, long long ldb, double* C,
                     long long ldc, int M, int N, int K, double alpha, double beta, int lower, int slices,
                     int same_operand, void* ws, long long ws_bytes, void* stream);

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "plmc_mix_tasks": [P, P, LL, P, P, P, P, LL, I, I, I, P],
     "plmc_gemm": [I, P, LL, LL, P, LL, LL, P, LL, LL, I, I, I, D, D, I, I, I, I, P],
     "plmc_ozaki_ws_bytes": [I, I, I, I, I],
+    "plmc_set_fp64_emulation": [P, LL, I, I],
     "plmc_ozaki_gemm": [I, P, LL, P, LL, P, LL, I, I, I, D, D, I, I, I, P, LL, P],
     "plmc_peak_dmma": [I, I, LL, P, P],
     "plmc_peak_dfma": [I, I, LL, P, P],

@@ -56,9 +56,33 @@ __global__ void __launch_bounds__(1024) quad_logdet_kernel(const double* __restr
 
 }  // namespace plmc
 
+// FP64-emulation configuration (process-wide; one process per GPU)
+static void* g_oz_ws = nullptr;
+static long long g_oz_bytes = 0;
+static int g_oz_slices = 0;
+static int g_oz_min = 1024;
+
+static LaCtx make_ctx(cudaStream_t st, int batch) {
+    LaCtx cx{st, batch, 0};
+    cx.oz_ws = g_oz_ws;
+    cx.oz_bytes = g_oz_bytes;
+    cx.oz_slices = g_oz_slices;
+    cx.oz_min = g_oz_min;
+    return cx;
+}
+
 extern "C" {
 
 int plmc_version(void) { return 100; }
+
+int plmc_set_fp64_emulation(void* ws, long long ws_bytes, int slices, int min_dim) {
+    if (slices < 0 || slices > 7 || (slices > 0 && (!ws || ws_bytes <= 0)) || min_dim < 128) return PLMC_ERR_BADARG;
+    g_oz_ws = ws;
+    g_oz_bytes = ws_bytes;
+    g_oz_slices = slices;
+    g_oz_min = min_dim;
+    return PLMC_OK;
+}
 
 int plmc_init(void) { return gemm_init_attrs(); }
 
@@ -101,7 +125,7 @@ int plmc_potrf_batched(double* K, long long ld, long long stride, long long npad
     if (bad_mat(K, ld, npad, batch) || !dinv || !info) return PLMC_ERR_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (cudaMemsetAsync(info, 0, sizeof(int) * batch, st) != cudaSuccess) return PLMC_ERR_LAUNCH;
-    LaCtx cx{st, batch, 0};
+    LaCtx cx = make_ctx(st, batch);
     potrf_lower(cx, BMat{K, ld, stride}, (int)npad, DinvBuf{dinv, npad * 128}, 0, info);
     return cx.status;
 }
@@ -110,7 +134,7 @@ int plmc_trsm_batched(int op, const double* L, long long ld, long long stride, l
                       const double* dinv, double* B, long long ldb, long long strideb, long long m, double alpha,
                       void* stream) {
     if (bad_mat(L, ld, npad, batch) || !dinv || !B || m <= 0 || (m % 128) || (ldb & 1)) return PLMC_ERR_BADARG;
-    LaCtx cx{(cudaStream_t)stream, batch, 0};
+    LaCtx cx = make_ctx((cudaStream_t)stream, batch);
     BMat Lm{const_cast<double*>(L), ld, stride};
     DinvBuf D{const_cast<double*>(dinv), npad * 128};
     BMat Bm{B, ldb, strideb};
@@ -134,7 +158,7 @@ int plmc_solve_logdet(const double* L, long long ld, long long stride, long long
     const int gx = (int)((npad * 128 + 255) / 256 < 1184 ? (npad * 128 + 255) / 256 : 1184);
     pack_rhs_kernel<<<dim3(gx, 1, batch), 256, 0, st>>>(y, ldy, rhs, n, npad);
     PLMC_CHECK_LAUNCH();
-    LaCtx cx{st, batch, 0};
+    LaCtx cx = make_ctx(st, batch);
     BMat Lm{const_cast<double*>(L), ld, stride};
     DinvBuf D{const_cast<double*>(dinv), npad * 128};
     BMat R{rhs, 128, npad * 128};
@@ -156,14 +180,14 @@ int plmc_solve_logdet(const double* L, long long ld, long long stride, long long
 int plmc_trtri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
                        void* stream) {
     if (bad_mat(L, ld, npad, batch) || !dinv) return PLMC_ERR_BADARG;
-    LaCtx cx{(cudaStream_t)stream, batch, 0};
+    LaCtx cx = make_ctx((cudaStream_t)stream, batch);
     trtri_lower(cx, BMat{L, ld, stride}, (int)npad, DinvBuf{const_cast<double*>(dinv), npad * 128}, 0);
     return cx.status;
 }
 
 int plmc_lauum_batched(double* L, long long ld, long long stride, long long npad, int batch, void* stream) {
     if (bad_mat(L, ld, npad, batch)) return PLMC_ERR_BADARG;
-    LaCtx cx{(cudaStream_t)stream, batch, 0};
+    LaCtx cx = make_ctx((cudaStream_t)stream, batch);
     lauum_lower(cx, BMat{L, ld, stride}, (int)npad);
     return cx.status;
 }

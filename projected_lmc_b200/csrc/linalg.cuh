@@ -23,7 +23,17 @@ struct LaCtx {
     cudaStream_t st;
     int batch;
     int status;  // first non-zero launch status
+    // FP64-via-INT8 (tcgen05, csrc/ozaki.cu) for the large GEMMs of the recursion; 0 slices = off
+    void* oz_ws = nullptr;
+    long long oz_bytes = 0;
+    int oz_slices = 0;
+    int oz_min = 1024;  // smallest M, N, K routed to the INT8 path
 };
+
+long long ozaki_ws_bytes(int M, int N, int K, int s, bool same_operand);
+int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, const double* B, long long ldb, double* C,
+               long long ldc, int M, int N, int K, double alpha, double beta, int lower, int s, bool same_operand,
+               void* ws, long long ws_bytes, cudaStream_t st);
 
 // Dinv: per batch member, n/128 consecutive 128x128 row-major blocks holding
 // inv(L_kk) (upper part explicitly zero).  stride = (n/128)*16384.

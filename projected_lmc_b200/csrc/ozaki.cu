@@ -115,7 +115,7 @@ struct OzArgs {
     int M, N, K;    // K % 32 == 0
     int s;          // planes (1..7)
     double alpha;
-    int beta_one;   // 1: C += ..., 0: C = ...
+    double beta;    // C = alpha * A B + beta * C   (C is not read when beta == 0)
     int lower;      // skip tiles entirely above the diagonal (C origin on the diagonal)
 };
 
@@ -127,7 +127,21 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     __shared__ uint32_t tmem_base_sh;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * OZ_BM, n0 = blockIdx.x * OZ_BN;
+    // grouped raster: bands of 8 tile-rows walk the columns together, so the ~148 CTAs in flight
+    // share 8 A row-blocks and ~18 B column-blocks out of L2 instead of streaming all of B
+    int tm, tn;
+    {
+        const int tiles_m = p.M / OZ_BM, tiles_n = p.N / OZ_BN;
+        const int GROUP = 8;
+        const int per_group = GROUP * tiles_n;
+        const int gid = blockIdx.x / per_group;
+        const int first = gid * GROUP;
+        const int gsz = min(tiles_m - first, GROUP);
+        const int rem = blockIdx.x - gid * per_group;
+        tm = first + rem % gsz;
+        tn = rem / gsz;
+    }
+    const int m0 = tm * OZ_BM, n0 = tn * OZ_BN;
     if (p.lower && n0 > m0 + OZ_BM - 1) return;   // whole CTA exits before any barrier / allocation
 
     const int s = p.s;
@@ -209,7 +223,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         for (int ch = 0; ch < nchunks; ++ch) {
             mbar_wait_(smem_u32(&acc_full), ch & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const bool add = p.beta_one || ch > 0;
+            const double beta = (ch > 0) ? 1.0 : p.beta;   // later K-chunks accumulate onto the first
 #pragma unroll 1
             for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
                 double v[16];
@@ -228,10 +242,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
                     const double f0 = scalbn(sa, p.eb[col]), f1 = scalbn(sa, p.eb[col + 1]);
                     double2 out = make_double2(p.alpha * f0 * v[j], p.alpha * f1 * v[j + 1]);
                     double2* dst = reinterpret_cast<double2*>(crow + c0 + j);
-                    if (add) {
+                    if (beta != 0.0) {
                         const double2 old = *dst;
-                        out.x += old.x;
-                        out.y += old.y;
+                        out.x = fma(beta, old.x, out.x);
+                        out.y = fma(beta, old.y, out.y);
                     }
                     *dst = out;
                 }
@@ -378,13 +392,12 @@ long long ozaki_ws_bytes(int M, int N, int K, int s, bool same_operand) {
     return ((a + pad - 1) / pad) * pad + ((b + pad - 1) / pad) * pad + 4LL * (M + N) + 2 * pad;
 }
 
-// C = alpha * op(A) op(B) + beta * C   (beta in {0, 1}),  one batch member.
+// C = alpha * op(A) op(B) + beta * C,  one batch member.
 // aKC / bKC as in gemm_dmma (bKC: B(k,n) at B[n*ldb+k]).  same_operand: op(B)^T == op(A) (SYRK).
 int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, const double* B, long long ldb, double* C,
                long long ldc, int M, int N, int K, double alpha, double beta, int lower, int s, bool same_operand,
                void* ws, long long ws_bytes, cudaStream_t st) {
-    if (s < 1 || s > OZ_SMAX || (M % OZ_BM) || (N % OZ_BN) || (K % 32) || (beta != 0.0 && beta != 1.0))
-        return PLMC_ERR_BADARG;
+    if (s < 1 || s > OZ_SMAX || (M % OZ_BM) || (N % OZ_BN) || (K % 32)) return PLMC_ERR_BADARG;
     if (same_operand && (M != N)) return PLMC_ERR_BADARG;
     if (ws_bytes < ozaki_ws_bytes(M, N, K, s, same_operand)) return PLMC_ERR_BADARG;
     if (get_encode()) return PLMC_ERR_LAUNCH;
@@ -422,8 +435,8 @@ int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, const double*
     OzArgs p;
     p.C = C; p.ldc = ldc; p.ea = ea; p.eb = eb;
     p.M = M; p.N = N; p.K = K; p.s = s;
-    p.alpha = alpha; p.beta_one = (beta == 1.0); p.lower = lower;
-    ozaki_gemm_kernel<<<dim3(N / OZ_BN, M / OZ_BM), OZ_THREADS, smem, st>>>(mapA, mapB, p);
+    p.alpha = alpha; p.beta = beta; p.lower = lower;
+    ozaki_gemm_kernel<<<(unsigned)((N / OZ_BN) * (M / OZ_BM)), OZ_THREADS, smem, st>>>(mapA, mapB, p);
     PLMC_CHECK_LAUNCH();
     note_launch(3);
     return PLMC_OK;

@@ -249,3 +249,11 @@ def ozaki_gemm(layout, A, B, C, M, N, K, alpha=1.0, beta=0.0, lower=False, slice
         "ozaki_gemm",
     )
     return C
+
+
+def set_fp64_emulation(ws, slices: int, min_dim: int = 1024):
+    """Route the large GEMMs of potrf/trsm/trtri/lauum through the tcgen05 INT8 path (slices=0: off)."""
+    if ws is None or slices == 0:
+        check(lib().plmc_set_fp64_emulation(None, 0, 0, max(128, min_dim)), "set_fp64_emulation")
+    else:
+        check(lib().plmc_set_fp64_emulation(ptr(ws), ws.numel(), slices, max(128, min_dim)), "set_fp64_emulation")

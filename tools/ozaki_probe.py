@@ -63,6 +63,6 @@ else:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); ops.ozaki_gemm(0, A, B, C, n, n, n, slices=s, ws=ws); e1.record(); torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
-        ref = A @ B
+        ref = A @ B.T          # layout 0: B(k, n) stored at B[n, k]
         print(f"n={n} s={s}: {best:.2f} ms  {2 * n ** 3 / best / 1e9:.1f} TFLOP/s (FP64-equivalent)  "
               f"rel err {((C - ref).abs().max() / ref.abs().max()).item():.2e}", flush=True)
