@@ -159,6 +159,46 @@ def dmma_peak_tflops():
     return best
 
 
+def roofline_entry(eng, achieved, dmma_peak, peaks, peak_src, gemm_flops, gemm_launches, fact_ms, steps):
+    """Roofline of the dominant kernel of the step (the O(n^3) factorisation layer).
+
+    achieved = algorithmic q*n^3 FLOP per step / CUDA-event time of the potrf + solve + potri phases.
+    With the FP64-via-INT8 path on (default), the large GEMMs run in ozaki_gemm_kernel on the tcgen05 INT8
+    tensor path: one FP64 product = s(s+1)/2 INT8 products, so the tensor roofline is (INT8 dense rate) /
+    (s(s+1)/2); the INT8 rate is taken as twice the MEASURED bf16 rate of MEASURED_PEAKS.json (kind::i8 issues
+    at twice the kind::f16 rate).  The FP64 DMMA peak (live microbenchmark) is reported next to it."""
+    s = getattr(eng, "fp64_slices", 0)
+    common = {
+        "bound": "tensor", "achieved": achieved, "unit": "TFLOP/s", "traffic": None,
+        "fp64_dmma_peak": dmma_peak, "vs_fp64_dmma_peak": (achieved / dmma_peak) if achieved else None,
+        "executed_dmma_gemm_tflops": gemm_flops / steps / (fact_ms * 1e-3) / 1e12 if fact_ms > 0 else None,
+        "dmma_gemm_launches_per_step": gemm_launches / steps,
+        "traffic_reference": "ncu --set full, one 8192^3 gemm_dmma_kernel launch: 6.77 GB read + 0.53 GB written "
+                             "(1.61 GB algorithmic) at 0.23 TB/s: not traffic bound (profiles/r01_gemm_dmma_ncu_full.txt)",
+    }
+    if s > 0:
+        pairs = s * (s + 1) // 2
+        bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
+        peak = 2.0 * bf16 / pairs
+        common.update({
+            "kernel": "ozaki_gemm_kernel (FP64 GEMM as %d INT8 tcgen05.mma products, TMA + TMEM) for GEMMs >= %d; "
+                      "gemm_dmma_kernel (DMMA.8x8x4) below" % (pairs, eng.fp64_min_dim),
+            "peak": peak, "frac": (achieved / peak) if achieved else None,
+            "peak_source": "2 x %s bf16 sustained (%.0f TFLOP/s) / %d INT8 products per FP64 product (%d slices)"
+                           % (peak_src, bf16, pairs, s),
+            "how": "algorithmic q*n^3 FLOP per step / CUDA-event time of the potrf+solve+potri phases",
+        })
+    else:
+        common.update({
+            "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4; potrf/trsm/trtri/lauum)",
+            "peak": dmma_peak, "frac": (achieved / dmma_peak) if achieved else None,
+            "peak_source": "live register-resident DMMA microbenchmark on this GPU (FP64 is absent from "
+                           "MEASURED_PEAKS.json)",
+            "how": "algorithmic q*n^3 FLOP per step / CUDA-event time of the potrf+solve+potri phases",
+        })
+    return common
+
+
 def oracle_iteration_time(cfg, n_s, steps, warmup, world=1):
     """The reference's algorithm (Cholesky-forced gpytorch semantics, restated in oracle/) on the host cores.
     `world` scales the model like the GPU arm does (4 latents / 7 tasks per GPU)."""
@@ -356,16 +396,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, cfg, world),
             "loss": float(loss.item()),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-            "roofline": {
-                "bound": "tensor", "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4; potrf/trsm/trtri/lauum)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": None,
-                "how": "algorithmic q*n^3 FLOP per step / CUDA-event time of the potrf+solve+potri phases "
-                       "(>95% of which is this kernel); peak = live register-resident DMMA microbenchmark on this "
-                       "GPU (FP64 is absent from MEASURED_PEAKS.json)",
-                "executed_gemm_tflops": gemm_flops / args.steps / (fact_ms * 1e-3) / 1e12 if fact_ms > 0 else None,
-                "gemm_launches_per_step": gemm_launches / args.steps,
-            },
+            "roofline": roofline_entry(eng, achieved, peak, peaks, peak_src, gemm_flops, gemm_launches, fact_ms,
+                                       args.steps),
             "roofline_secondary": [{
                 "kernel": "gram_kernel (fused ARD Gram build)", "bound": "hbm",
                 "achieved": gram_bytes / (phases.get("gram", 0.0) / args.steps * 1e-3) / 1e9 if phases.get("gram") else None,

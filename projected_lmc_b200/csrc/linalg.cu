@@ -35,14 +35,12 @@ static void gemm(LaCtx& cx, bool aKC, bool bKC, BMat A, BMat B, BMat C, int M, i
                  double beta, int lower = 0, int triA = 0, int triB = 0) {
     if (cx.status) return;
     if (cx.oz_slices > 0 && !triA && !triB && M >= cx.oz_min && N >= cx.oz_min && K >= cx.oz_min) {
-        // large update: FP64 product through the INT8 tensor path, one batch member at a time
-        // (they share the plane workspace; everything is ordered on the one stream)
+        // large update: FP64 product through the INT8 tensor path (all batch members per launch when
+        // the plane scratch holds them, otherwise in passes; everything is ordered on the one stream)
         const bool same = (A.p == B.p && A.ld == B.ld && aKC == bKC && M == N);
-        if (ozaki_ws_bytes(M, N, K, cx.oz_slices, same) <= cx.oz_bytes) {
-            for (int b = 0; b < cx.batch && !cx.status; ++b)
-                cx.status = ozaki_gemm(aKC, bKC, A.p + b * A.stride, A.ld, B.p + b * B.stride, B.ld,
-                                       C.p + b * C.stride, C.ld, M, N, K, alpha, beta, lower, cx.oz_slices, same,
-                                       cx.oz_ws, cx.oz_bytes, cx.st);
+        if (ozaki_ws_bytes(M, N, K, cx.oz_slices, same) + 1024 <= cx.oz_bytes) {
+            cx.status = ozaki_gemm(aKC, bKC, A.p, A.ld, A.stride, B.p, B.ld, B.stride, C.p, C.ld, C.stride, M, N, K,
+                                   alpha, beta, lower, cx.oz_slices, same, cx.batch, cx.oz_ws, cx.oz_bytes, cx.st);
             return;
         }
     }

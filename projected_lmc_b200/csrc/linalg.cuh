@@ -31,9 +31,9 @@ struct LaCtx {
 };
 
 long long ozaki_ws_bytes(int M, int N, int K, int s, bool same_operand);
-int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, const double* B, long long ldb, double* C,
-               long long ldc, int M, int N, int K, double alpha, double beta, int lower, int s, bool same_operand,
-               void* ws, long long ws_bytes, cudaStream_t st);
+int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA, const double* B, long long ldb,
+               long long sB, double* C, long long ldc, long long sC, int M, int N, int K, double alpha, double beta,
+               int lower, int s, bool same_operand, int batch, void* ws, long long ws_bytes, cudaStream_t st);
 
 // Dinv: per batch member, n/128 consecutive 128x128 row-major blocks holding
 // inv(L_kk) (upper part explicitly zero).  stride = (n/128)*16384.

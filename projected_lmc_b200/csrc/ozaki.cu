@@ -59,11 +59,11 @@ __device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                            int c2) {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
@@ -109,9 +109,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 
 struct OzArgs {
     double* C;
-    long long ldc;
-    const int* ea;  // [M] row exponents of op(A)
-    const int* eb;  // [N] column exponents of op(B)
+    long long ldc, sC;   // leading dimension and batch stride of C (elements)
+    const int* ea;  // [batch][M] row exponents of op(A)
+    const int* eb;  // [batch][N] column exponents of op(B)
     int M, N, K;    // K % 32 == 0
     int s;          // planes (1..7)
     double alpha;
@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     __shared__ uint32_t tmem_base_sh;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bz = blockIdx.z;   // batch member
     // grouped raster: bands of 8 tile-rows walk the columns together, so the ~148 CTAs in flight
     // share 8 A row-blocks and ~18 B column-blocks out of L2 instead of streaming all of B
     int tm, tn;
@@ -180,8 +181,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
                 mbar_expect_tx_(fb, (uint32_t)stage_bytes);
                 const uint32_t sa = smem0 + (uint32_t)st * stage_bytes;
                 const uint32_t sb = sa + (uint32_t)s * OZ_A_PLANE;
-                for (int i = 0; i < s; ++i) tma_load_3d(sa + i * OZ_A_PLANE, &mapA, fb, kt * OZ_BK, m0, i);
-                for (int j = 0; j < s; ++j) tma_load_3d(sb + j * OZ_B_PLANE, &mapB, fb, kt * OZ_BK, n0, j);
+                for (int i = 0; i < s; ++i) tma_load_4d(sa + i * OZ_A_PLANE, &mapA, fb, kt * OZ_BK, m0, i, bz);
+                for (int j = 0; j < s; ++j) tma_load_4d(sb + j * OZ_B_PLANE, &mapB, fb, kt * OZ_BK, n0, j, bz);
             }
         }
     } else if (warp == 1) {
@@ -200,13 +201,21 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
                 if (elect_one()) {
                     const uint32_t sa = smem0 + (uint32_t)st * stage_bytes;
                     const uint32_t sb = sa + (uint32_t)s * OZ_A_PLANE;
+                    // Plane A_i meets B_0 .. B_{s-1-i}; their products belong to the accumulators of the
+                    // diagonals g = i .. s-1, which are CONSECUTIVE 64-column blocks of TMEM, and the B planes
+                    // are consecutive 64-row blocks of shared memory.  So all pairs of one i are a single
+                    // wide MMA (N = 64 (s-i), split at the instruction limit N = 256): A_i is read from shared
+                    // memory once instead of s-i times -- the N = 64 form is shared-memory-bandwidth bound.
                     for (int i = 0; i < s; ++i) {
                         const uint64_t da = umma_desc_sw32(sa + i * OZ_A_PLANE);
-                        for (int j = 0; i + j < s; ++j) {
-                            const uint64_t db = umma_desc_sw32(sb + j * OZ_B_PLANE);
-                            // accumulator of diagonal g = i + j; first write of the chunk: pair (0, g) at kt0
-                            umma_i8(tmem_base + (uint32_t)(i + j) * OZ_BN, da, db, idesc, (kt > kt0 || i > 0) ? 1u : 0u);
-                        }
+                        const int nplanes = s - i;
+                        const uint32_t accum = (kt > kt0 || i > 0) ? 1u : 0u;   // i = 0 touches every accumulator
+                        const int np1 = nplanes < 4 ? nplanes : 4;
+                        umma_i8(tmem_base + (uint32_t)i * OZ_BN, da, umma_desc_sw32(sb),
+                                umma_idesc_i8(OZ_BM, OZ_BN * np1), accum);
+                        if (nplanes > 4)
+                            umma_i8(tmem_base + (uint32_t)(i + 4) * OZ_BN, da, umma_desc_sw32(sb + 4 * OZ_B_PLANE),
+                                    umma_idesc_i8(OZ_BM, OZ_BN * (nplanes - 4)), accum);
                     }
                     umma_commit(smem_u32(&empty_bar[st]));            // frees the smem stage when the MMAs retire
                     if (kt == kt1 - 1) umma_commit(smem_u32(&acc_full));  // accumulators complete for this chunk
@@ -218,8 +227,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         // ===== epilogue: TMEM -> registers -> FP64 recombination -> C =====
         const int quad = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = m0 + quad * 32 + lane;
-        const double sa = scalbn(1.0, p.ea[row] - 14);
-        double* crow = p.C + (long long)row * p.ldc + n0;
+        const double sa = scalbn(1.0, p.ea[(long long)bz * p.M + row] - 14);
+        const int* ebz = p.eb + (long long)bz * p.N;
+        double* crow = p.C + (long long)bz * p.sC + (long long)row * p.ldc + n0;
         for (int ch = 0; ch < nchunks; ++ch) {
             mbar_wait_(smem_u32(&acc_full), ch & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -239,7 +249,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                     const int col = n0 + c0 + j;
-                    const double f0 = scalbn(sa, p.eb[col]), f1 = scalbn(sa, p.eb[col + 1]);
+                    const double f0 = scalbn(sa, ebz[col]), f1 = scalbn(sa, ebz[col + 1]);
                     double2 out = make_double2(p.alpha * f0 * v[j], p.alpha * f1 * v[j + 1]);
                     double2* dst = reinterpret_cast<double2*>(crow + c0 + j);
                     if (beta != 0.0) {
@@ -275,11 +285,15 @@ __device__ __forceinline__ int exp_for(double amax) {
 }
 
 // one CTA per row (KC): coalesced along k
-__global__ void __launch_bounds__(256) slice_kc_kernel(const double* __restrict__ P, long long ld, int X, int K,
-                                                       int s, int8_t* __restrict__ planes, int* __restrict__ ex) {
+__global__ void __launch_bounds__(256) slice_kc_kernel(const double* __restrict__ Pb, long long ld, long long sP,
+                                                       int X, int K, int s, int8_t* __restrict__ planes_b,
+                                                       int* __restrict__ ex_b) {
     __shared__ double red[8];
     __shared__ int e_sh;
     const int x = blockIdx.x;
+    const double* P = Pb + (long long)blockIdx.z * sP;
+    int8_t* planes = planes_b + (long long)blockIdx.z * s * X * K;
+    int* ex = ex_b + (long long)blockIdx.z * X;
     const double* row = P + (long long)x * ld;
     double amax = 0.0;
     for (int k = threadIdx.x; k < K; k += 256) amax = fmax(amax, fabs(row[k]));
@@ -316,20 +330,25 @@ __global__ void __launch_bounds__(256) slice_kc_kernel(const double* __restrict_
 }
 
 // MC operand, pass 1: column-wise absmax over k   (threads along x: coalesced)
-__global__ void __launch_bounds__(256) absmax_mc_kernel(const double* __restrict__ P, long long ld, int X, int K,
-                                                        int* __restrict__ ex) {
+__global__ void __launch_bounds__(256) absmax_mc_kernel(const double* __restrict__ Pb, long long ld, long long sP,
+                                                        int X, int K, int* __restrict__ ex_b) {
     const int x = blockIdx.x * 256 + threadIdx.x;
     if (x >= X) return;
+    const double* P = Pb + (long long)blockIdx.z * sP;
+    int* ex = ex_b + (long long)blockIdx.z * X;
     double amax = 0.0;
     for (int k = 0; k < K; ++k) amax = fmax(amax, fabs(P[(long long)k * ld + x]));
     ex[x] = exp_for(amax);
 }
 
 // MC operand, pass 2: 32(k) x 32(x) tiles transposed through shared memory
-__global__ void __launch_bounds__(256) slice_mc_kernel(const double* __restrict__ P, long long ld, int X, int K,
-                                                       int s, int8_t* __restrict__ planes,
-                                                       const int* __restrict__ ex) {
+__global__ void __launch_bounds__(256) slice_mc_kernel(const double* __restrict__ Pb, long long ld, long long sP,
+                                                       int X, int K, int s, int8_t* __restrict__ planes_b,
+                                                       const int* __restrict__ ex_b) {
     __shared__ double tile[32][33];
+    const double* P = Pb + (long long)blockIdx.z * sP;
+    int8_t* planes = planes_b + (long long)blockIdx.z * s * X * K;
+    const int* ex = ex_b + (long long)blockIdx.z * X;
     const int x0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows of 32
     for (int r = ty; r < 32; r += 8) tile[r][tx] = P[(long long)(k0 + r) * ld + x0 + tx];   // tile[k][x]
@@ -372,13 +391,14 @@ static int get_encode() {
     return PLMC_OK;
 }
 
-// planes [s][X][K] int8 -> 3-D map, box {32 B, box_rows, 1}, SWIZZLE_32B
-static int make_plane_map(CUtensorMap* map, const int8_t* planes, int X, int K, int s, int box_rows) {
-    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)X, (cuuint64_t)s};
-    const cuuint64_t strides[2] = {(cuuint64_t)K, (cuuint64_t)K * (cuuint64_t)X};
-    const cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)planes, dims, strides, box, estr,
+// planes [batch][s][X][K] int8 -> 4-D map, box {32 B, box_rows, 1, 1}, SWIZZLE_32B
+static int make_plane_map(CUtensorMap* map, const int8_t* planes, int X, int K, int s, int batch, int box_rows) {
+    const cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)X, (cuuint64_t)s, (cuuint64_t)batch};
+    const cuuint64_t strides[3] = {(cuuint64_t)K, (cuuint64_t)K * (cuuint64_t)X,
+                                   (cuuint64_t)K * (cuuint64_t)X * (cuuint64_t)s};
+    const cuuint32_t box[4] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, 1, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)planes, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? PLMC_OK : PLMC_ERR_LAUNCH;
@@ -386,59 +406,67 @@ static int make_plane_map(CUtensorMap* map, const int8_t* planes, int X, int K, 
 
 static bool g_oz_attr = false;
 
+// scratch for ONE batch member (planes of both operands + exponents)
 long long ozaki_ws_bytes(int M, int N, int K, int s, bool same_operand) {
     const long long a = (long long)s * M * K, b = same_operand ? 0 : (long long)s * N * K;
     const long long pad = 1024;
-    return ((a + pad - 1) / pad) * pad + ((b + pad - 1) / pad) * pad + 4LL * (M + N) + 2 * pad;
+    return ((a + pad - 1) / pad) * pad + ((b + pad - 1) / pad) * pad + ((4LL * (M + N) + pad - 1) / pad) * pad + pad;
 }
 
-// C = alpha * op(A) op(B) + beta * C,  one batch member.
+// C[b] = alpha * op(A[b]) op(B[b]) + beta * C[b]  for b < batch (as many members per pass as the scratch holds).
 // aKC / bKC as in gemm_dmma (bKC: B(k,n) at B[n*ldb+k]).  same_operand: op(B)^T == op(A) (SYRK).
-int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, const double* B, long long ldb, double* C,
-               long long ldc, int M, int N, int K, double alpha, double beta, int lower, int s, bool same_operand,
-               void* ws, long long ws_bytes, cudaStream_t st) {
-    if (s < 1 || s > OZ_SMAX || (M % OZ_BM) || (N % OZ_BN) || (K % 32)) return PLMC_ERR_BADARG;
+int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA, const double* B, long long ldb,
+               long long sB, double* C, long long ldc, long long sC, int M, int N, int K, double alpha, double beta,
+               int lower, int s, bool same_operand, int batch, void* ws, long long ws_bytes, cudaStream_t st) {
+    if (s < 1 || s > OZ_SMAX || (M % OZ_BM) || (N % OZ_BN) || (K % 32) || batch < 1) return PLMC_ERR_BADARG;
     if (same_operand && (M != N)) return PLMC_ERR_BADARG;
-    if (ws_bytes < ozaki_ws_bytes(M, N, K, s, same_operand)) return PLMC_ERR_BADARG;
-    if (get_encode()) return PLMC_ERR_LAUNCH;
     const long long pad = 1024;
-    uint8_t* w = (uint8_t*)ws;
-    w = (uint8_t*)(((uintptr_t)w + pad - 1) / pad * pad);
-    int8_t* pa = (int8_t*)w;
-    w += (((long long)s * M * K + pad - 1) / pad) * pad;
-    int8_t* pb = same_operand ? pa : (int8_t*)w;
-    if (!same_operand) w += (((long long)s * N * K + pad - 1) / pad) * pad;
-    int* ea = (int*)w;
-    int* eb = same_operand ? ea : ea + M;
-
-    auto slice = [&](bool kc, const double* P, long long ld, int X, int8_t* planes, int* ex) {
-        if (kc) {
-            slice_kc_kernel<<<X, 256, 0, st>>>(P, ld, X, K, s, planes, ex);
-        } else {
-            absmax_mc_kernel<<<(X + 255) / 256, 256, 0, st>>>(P, ld, X, K, ex);
-            slice_mc_kernel<<<dim3(X / 32, K / 32), 256, 0, st>>>(P, ld, X, K, s, planes, ex);
-        }
-    };
-    slice(aKC, A, lda, M, pa, ea);
-    if (!same_operand) slice(bKC, B, ldb, N, pb, eb);
-    PLMC_CHECK_LAUNCH();
-
-    CUtensorMap mapA, mapB;
-    if (make_plane_map(&mapA, pa, M, K, s, OZ_BM) || make_plane_map(&mapB, pb, N, K, s, OZ_BN)) return PLMC_ERR_LAUNCH;
-    const int smem = OZ_STAGES * oz_stage_bytes(s) + 1024;
+    uint8_t* w0 = (uint8_t*)(((uintptr_t)ws + pad - 1) / pad * pad);
+    const long long avail = ws_bytes - (long long)(w0 - (uint8_t*)ws);
+    const long long need1 = ozaki_ws_bytes(M, N, K, s, same_operand);
+    if (avail < need1) return PLMC_ERR_BADARG;
+    if (get_encode()) return PLMC_ERR_LAUNCH;
+    const int bc_max = (int)((avail / need1) < batch ? (avail / need1) : batch);
+    const long long bytesA = (((long long)s * M * K + pad - 1) / pad) * pad;
+    const long long bytesB = same_operand ? 0 : (((long long)s * N * K + pad - 1) / pad) * pad;
     if (!g_oz_attr) {
         if (cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  OZ_STAGES * oz_stage_bytes(OZ_SMAX) + 1024) != cudaSuccess)
             return PLMC_ERR_LAUNCH;
         g_oz_attr = true;
     }
-    OzArgs p;
-    p.C = C; p.ldc = ldc; p.ea = ea; p.eb = eb;
-    p.M = M; p.N = N; p.K = K; p.s = s;
-    p.alpha = alpha; p.beta = beta; p.lower = lower;
-    ozaki_gemm_kernel<<<(unsigned)((N / OZ_BN) * (M / OZ_BM)), OZ_THREADS, smem, st>>>(mapA, mapB, p);
-    PLMC_CHECK_LAUNCH();
-    note_launch(3);
+    const int smem = OZ_STAGES * oz_stage_bytes(s) + 1024;
+
+    for (int b0 = 0; b0 < batch; b0 += bc_max) {
+        const int bc = (batch - b0) < bc_max ? (batch - b0) : bc_max;
+        // layout of the scratch for this pass: A planes [bc][s][M][K] | B planes [bc][s][N][K] | ea [bc][M] | eb [bc][N]
+        // (member planes are contiguous: the per-member byte counts are NOT padded inside the 4-D maps)
+        int8_t* pa = (int8_t*)w0;
+        int8_t* pb = same_operand ? pa : (int8_t*)(w0 + bytesA * bc);
+        int* ea = (int*)(w0 + (bytesA + bytesB) * bc);
+        int* eb = same_operand ? ea : ea + (long long)bc * M;
+        auto slice = [&](bool kc, const double* P, long long ld, long long sP, int X, int8_t* planes, int* ex) {
+            if (kc) {
+                slice_kc_kernel<<<dim3(X, 1, bc), 256, 0, st>>>(P, ld, sP, X, K, s, planes, ex);
+            } else {
+                absmax_mc_kernel<<<dim3((X + 255) / 256, 1, bc), 256, 0, st>>>(P, ld, sP, X, K, ex);
+                slice_mc_kernel<<<dim3(X / 32, K / 32, bc), 256, 0, st>>>(P, ld, sP, X, K, s, planes, ex);
+            }
+        };
+        slice(aKC, A + (long long)b0 * sA, lda, sA, M, pa, ea);
+        if (!same_operand) slice(bKC, B + (long long)b0 * sB, ldb, sB, N, pb, eb);
+        PLMC_CHECK_LAUNCH();
+        CUtensorMap mapA, mapB;
+        if (make_plane_map(&mapA, pa, M, K, s, bc, OZ_BM) || make_plane_map(&mapB, pb, N, K, s, bc, OZ_BN))
+            return PLMC_ERR_LAUNCH;
+        OzArgs p;
+        p.C = C + (long long)b0 * sC; p.ldc = ldc; p.sC = sC; p.ea = ea; p.eb = eb;
+        p.M = M; p.N = N; p.K = K; p.s = s;
+        p.alpha = alpha; p.beta = beta; p.lower = lower;
+        ozaki_gemm_kernel<<<dim3((unsigned)((N / OZ_BN) * (M / OZ_BM)), 1, bc), OZ_THREADS, smem, st>>>(mapA, mapB, p);
+        PLMC_CHECK_LAUNCH();
+        note_launch(3);
+    }
     return PLMC_OK;
 }
 
@@ -455,7 +483,7 @@ int plmc_ozaki_gemm(int layout, const double* A, long long lda, const double* B,
                     int same_operand, void* ws, long long ws_bytes, void* stream) {
     if (!A || !B || !C || !ws) return PLMC_ERR_BADARG;
     const bool aKC = !(layout & 2), bKC = !(layout & 1);
-    return plmc::ozaki_gemm(aKC, bKC, A, lda, B, ldb, C, ldc, M, N, K, alpha, beta, lower, slices, same_operand != 0,
-                            ws, ws_bytes, (cudaStream_t)stream);
+    return plmc::ozaki_gemm(aKC, bKC, A, lda, 0, B, ldb, 0, C, ldc, 0, M, N, K, alpha, beta, lower, slices,
+                            same_operand != 0, 1, ws, ws_bytes, (cudaStream_t)stream);
 }
 }

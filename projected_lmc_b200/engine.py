@@ -51,7 +51,7 @@ class LatentEngine:
             )
             self._ws_key = key
             self._oz = None
-        self._configure_fp64(device, np_)
+        self._configure_fp64(device, np_, q)
         return self._ws
 
     # -- FP64 through the INT8 tensor path (csrc/ozaki.cu) for the large GEMMs ------------------
@@ -59,15 +59,19 @@ class LatentEngine:
     # GEMM dimension routed to the INT8 path.  Defaults come from the environment so that the
     # whole test-suite can be run in either mode.
     fp64_slices = int(__import__("os").environ.get("PLMC_FP64_SLICES", "7"))
-    fp64_min_dim = int(__import__("os").environ.get("PLMC_FP64_MIN_DIM", "1024"))
+    fp64_min_dim = int(__import__("os").environ.get("PLMC_FP64_MIN_DIM", "2048"))
     _oz = None
 
-    def _configure_fp64(self, device, np_):
+    def _configure_fp64(self, device, np_, q=1):
         s, md = self.fp64_slices, self.fp64_min_dim
         if s <= 0 or np_ < 2 * md:
             ops.set_fp64_emulation(None, 0, md)
             return
-        need = s * (np_ // 2) * (np_ // 2 + 8192) + (1 << 20)
+        # planes of the largest GEMM of the recursion (s * (M + N) * K bytes, M, K <= npad/2, N <= npad/2
+        # or a prediction tile) for every latent, capped: the library works through the batch in passes
+        # when the scratch holds fewer members
+        per_member = s * (np_ // 2) * (np_ // 2 + 8192) + (1 << 20)
+        need = min(q * per_member, max(per_member, 24 << 30))
         if self._oz is None or self._oz.numel() < need or self._oz.device != device:
             self._oz = None
             self._oz = torch.empty((need,), dtype=torch.uint8, device=device)
@@ -220,7 +224,7 @@ class LatentEngine:
         np_ = st["L"].shape[1]
         ns = Xs.shape[0]
         dev = Xs.device
-        self._configure_fp64(dev, np_)
+        self._configure_fp64(dev, np_, q)
         mt_full = tile or self.tile_points(q, np_)
         lat_mean = torch.empty((q, ns), dtype=torch.float64, device=dev)
         lat_var = torch.empty((q, ns), dtype=torch.float64, device=dev) if need_var else None
