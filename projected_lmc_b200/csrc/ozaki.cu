@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         // ===== epilogue: TMEM -> registers -> FP64 recombination -> C =====
         const int quad = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = m0 + quad * 32 + lane;
-        const double sa = scalbn(1.0, p.ea[(long long)bz * p.M + row] - 14);
+        const double sa = scalbn(1.0, max(p.ea[(long long)bz * p.M + row], -1022) - 14);
         const int* ebz = p.eb + (long long)bz * p.N;
         double* crow = p.C + (long long)bz * p.sC + (long long)row * p.ldc + n0;
         for (int ch = 0; ch < nchunks; ++ch) {
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
                     const int col = n0 + c0 + j;
-                    const double f0 = scalbn(sa, ebz[col]), f1 = scalbn(sa, ebz[col + 1]);
+                    const double f0 = scalbn(sa, max(ebz[col], -1022)), f1 = scalbn(sa, max(ebz[col + 1], -1022));
                     double2 out = make_double2(p.alpha * f0 * v[j], p.alpha * f1 * v[j + 1]);
                     double2* dst = reinterpret_cast<double2*>(crow + c0 + j);
                     if (beta != 0.0) {
@@ -329,16 +329,32 @@ __global__ void __launch_bounds__(256) slice_kc_kernel(const double* __restrict_
     }
 }
 
-// MC operand, pass 1: column-wise absmax over k   (threads along x: coalesced)
+// MC operand, pass 1: exponent of the column-wise absmax over k.  The frexp exponent is monotone in
+// |x|, so the maximum of the per-element exponents is taken with an integer atomicMax over k-slabs
+// (order independent -> deterministic).  ex must be pre-set to a very negative value (memset 0x80).
 __global__ void __launch_bounds__(256) absmax_mc_kernel(const double* __restrict__ Pb, long long ld, long long sP,
                                                         int X, int K, int* __restrict__ ex_b) {
-    const int x = blockIdx.x * 256 + threadIdx.x;
-    if (x >= X) return;
+    __shared__ int red[4][64];
+    const int xl = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int x = blockIdx.x * 64 + xl;
     const double* P = Pb + (long long)blockIdx.z * sP;
     int* ex = ex_b + (long long)blockIdx.z * X;
-    double amax = 0.0;
-    for (int k = 0; k < K; ++k) amax = fmax(amax, fabs(P[(long long)k * ld + x]));
-    ex[x] = exp_for(amax);
+    const int k0 = blockIdx.y * 256, k1 = min(K, k0 + 256);
+    int emax = -2000000000;
+    if (x < X) {
+        for (int k = k0 + grp; k < k1; k += 4) {
+            const long long bits = __double_as_longlong(P[(long long)k * ld + x]);
+            const int be = (int)((bits >> 52) & 0x7FF);          // biased exponent; 0 for zero / subnormal
+            const int e = be ? be - 1022 : -1022;                   // frexp exponent (|x| * 2^-e in [0.5, 1))
+            if (bits << 1) emax = max(emax, e);                     // skip exact zeros
+        }
+    }
+    red[grp][xl] = emax;
+    __syncthreads();
+    if (grp == 0 && x < X) {
+        emax = max(max(red[0][xl], red[1][xl]), max(red[2][xl], red[3][xl]));
+        if (emax > -2000000000) atomicMax(ex + x, emax);
+    }
 }
 
 // MC operand, pass 2: 32(k) x 32(x) tiles transposed through shared memory
@@ -355,7 +371,7 @@ __global__ void __launch_bounds__(256) slice_mc_kernel(const double* __restrict_
     __syncthreads();
     // thread -> (x = threadIdx.x / 8, 4 consecutive k = (threadIdx.x % 8) * 4)
     const int xl = threadIdx.x >> 3, kl = (threadIdx.x & 7) * 4;
-    const int e = ex[x0 + xl];
+    const int e = max(ex[x0 + xl], -1022);   // all-zero column: any exponent works
     double v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = scalbn(tile[kl + u][xl], -e);
@@ -449,7 +465,8 @@ int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA,
             if (kc) {
                 slice_kc_kernel<<<dim3(X, 1, bc), 256, 0, st>>>(P, ld, sP, X, K, s, planes, ex);
             } else {
-                absmax_mc_kernel<<<dim3((X + 255) / 256, 1, bc), 256, 0, st>>>(P, ld, sP, X, K, ex);
+                cudaMemsetAsync(ex, 0x80, sizeof(int) * (size_t)X * bc, st);
+                absmax_mc_kernel<<<dim3((X + 63) / 64, (K + 255) / 256, bc), 256, 0, st>>>(P, ld, sP, X, K, ex);
                 slice_mc_kernel<<<dim3(X / 32, K / 32, bc), 256, 0, st>>>(P, ld, sP, X, K, s, planes, ex);
             }
         };
