@@ -1,4 +1,4 @@
-// FP64 GEMM through the 5th-generation tensor cores (tcgen05 / TMEM / TMA):
+// FP64 GEMM through the 5th-generation tensor cores (tcgen05 / TMEM / bulk async copies):
 // Ozaki-style error-free slicing of the FP64 operands into signed 8-bit planes,
 // exact INT8 x INT8 -> INT32 products on tcgen05.mma.kind::i8, FP64 recombination.
 //
@@ -12,13 +12,21 @@
 //   C[m,n] += alpha * 2^(ea[m]+eb[n]-14) * sum_{g<s} 2^-7g * D_g[m,n],
 //   D_g = sum_{i+j=g} A_i B_j^T   (INT32, exact for K-chunks <= 16384)
 //
-// Kernel: one CTA per 128 x 64 output tile; all s A-planes and s B-planes of a
-// 32-byte K-step are staged by TMA (SWIZZLE_32B) in a 5-stage mbarrier ring, one
-// elected thread issues the s(s+1)/2 MMAs per stage into s TMEM accumulators
-// (one per diagonal g, 64 columns each), four epilogue warps read TMEM back
-// (tcgen05.ld), recombine in FP64 and update C in place.
-#include <cuda.h>
-
+// Data layout ("tile images"): the slicers write the planes of an operand directly in the
+// order and byte pattern the tensor core wants in shared memory:
+//     planes[batch][x / 128][k / 32][plane][4096 B]
+// where one 4096-byte image is the canonical K-major SWIZZLE_32B UMMA tile of 128 rows x 32 bytes
+// (row r, 16-byte chunk c at  r*32 + ((c ^ ((r >> 2) & 1)) * 16)).  A stage of the pipeline is then
+// ONE contiguous 28 KB bulk copy for A plus s 2 KB copies for B (a 64-row B tile is one half of an
+// image), issued as cp.async.bulk with mbarrier completion: full 128-byte lines per request.  (The
+// first version used 4-D TMA tensor maps with 32-byte inner boxes and was bound by the
+// L1TEX->XBAR request rate, ncu: l1tex__m_l1tex2xbar_req_cycles_active 83 %.)
+//
+// Kernel: one CTA per 128 x 64 output tile; warp 0 = copy producer, warp 1 = MMA issuer
+// (one elected thread), warps 2..5 = epilogue.  s accumulators (one per diagonal g, 64
+// TMEM columns each, 448 of 512 columns at s = 7).  All pairs (i, j) of one A plane i are a
+// single wide MMA: their accumulators g = i..s-1 are consecutive TMEM column blocks and the
+// B planes consecutive shared-memory row blocks, so A_i is read from shared memory once.
 #include "plmc_common.cuh"
 
 namespace plmc {
@@ -26,12 +34,12 @@ namespace plmc {
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 32;   // BK in int8 elements = bytes
 constexpr int OZ_SMAX = 7;                           // TMEM: 7 accumulators x 64 columns = 448 <= 512
 constexpr int OZ_STAGES = 5;
-constexpr int OZ_THREADS = 192;                      // warp0 TMA, warp1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int OZ_THREADS = 192;                      // warp0 producer, warp1 MMA + TMEM alloc, warps 2..5 epilogue
 constexpr int OZ_KCHUNK = 16384;                     // INT32 exactness: 7 * 16384 * 127^2 < 2^31
-constexpr int OZ_A_PLANE = OZ_BM * OZ_BK;            // 4096 B
-constexpr int OZ_B_PLANE = OZ_BN * OZ_BK;            // 2048 B
+constexpr int OZ_IMG = OZ_BM * OZ_BK;                // 4096 B: one plane of one (128-row, 32-k) tile
+constexpr int OZ_B_PLANE = OZ_BN * OZ_BK;            // 2048 B: half an image
 
-__host__ __device__ inline int oz_stage_bytes(int s) { return s * (OZ_A_PLANE + OZ_B_PLANE); }
+__host__ __device__ inline int oz_stage_bytes(int s) { return s * (OZ_IMG + OZ_B_PLANE); }
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -59,12 +67,11 @@ __device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                            int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS UBLKCP)
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -107,21 +114,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
 }
 
+// byte offset of element (x, k) of plane i inside the tile-image layout of one batch member
+__device__ __forceinline__ long long img_offset(int x, int k, int i, int s, int nkt) {
+    const int tile = x >> 7, r = x & 127, kt = k >> 5, kk = k & 31;
+    const int c = kk >> 4, b = kk & 15;
+    return ((long long)((long long)tile * nkt + kt) * s + i) * OZ_IMG + r * 32 + ((c ^ ((r >> 2) & 1)) << 4) + b;
+}
+
 struct OzArgs {
     double* C;
-    long long ldc, sC;   // leading dimension and batch stride of C (elements)
-    const int* ea;  // [batch][M] row exponents of op(A)
-    const int* eb;  // [batch][N] column exponents of op(B)
-    int M, N, K;    // K % 32 == 0
-    int s;          // planes (1..7)
+    long long ldc, sC;      // leading dimension and batch stride of C (elements)
+    const int8_t* PA;       // tile images of op(A): [batch][M/128][K/32][s][4096]
+    const int8_t* PB;       // tile images of op(B): [batch][N/128][K/32][s][4096]
+    long long sPA, sPB;     // batch strides (bytes)
+    const int* ea;          // [batch][M] row exponents of op(A)
+    const int* eb;          // [batch][N] column exponents of op(B)
+    int M, N, K;            // M % 128 == 0, N % 128 == 0, K % 32 == 0
+    int s;                  // planes (1..7)
     double alpha;
-    double beta;    // C = alpha * A B + beta * C   (C is not read when beta == 0)
-    int lower;      // skip tiles entirely above the diagonal (C origin on the diagonal)
+    double beta;            // C = alpha * A B + beta * C   (C is not read when beta == 0)
+    int lower;              // skip tiles entirely above the diagonal (C origin on the diagonal)
 };
 
-__global__ void __launch_bounds__(OZ_THREADS, 1)
-    ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                      const OzArgs p) {
+__global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzArgs p) {
     extern __shared__ __align__(1024) uint8_t oz_smem[];
     __shared__ __align__(8) unsigned long long full_bar[OZ_STAGES], empty_bar[OZ_STAGES], acc_full, acc_empty;
     __shared__ uint32_t tmem_base_sh;
@@ -172,22 +187,25 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     const uint32_t tmem_base = tmem_base_sh;
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== copy producer: one 28 KB bulk copy (all A planes) + s 2 KB copies (B planes) per stage =====
         if (elect_one()) {
+            const int8_t* ga = p.PA + (long long)bz * p.sPA + (long long)tm * nkt * s * OZ_IMG;
+            // the 64-row B tile tn is half (tn & 1) of the image rows of 128-row tile tn >> 1
+            const int8_t* gb = p.PB + (long long)bz * p.sPB + (long long)(tn >> 1) * nkt * s * OZ_IMG + (tn & 1) * OZ_B_PLANE;
             for (int kt = 0; kt < nkt; ++kt) {
                 const int st = kt % OZ_STAGES, round = kt / OZ_STAGES;
                 if (round > 0) mbar_wait_(smem_u32(&empty_bar[st]), (round - 1) & 1);
                 const uint32_t fb = smem_u32(&full_bar[st]);
                 mbar_expect_tx_(fb, (uint32_t)stage_bytes);
                 const uint32_t sa = smem0 + (uint32_t)st * stage_bytes;
-                const uint32_t sb = sa + (uint32_t)s * OZ_A_PLANE;
-                for (int i = 0; i < s; ++i) tma_load_4d(sa + i * OZ_A_PLANE, &mapA, fb, kt * OZ_BK, m0, i, bz);
-                for (int j = 0; j < s; ++j) tma_load_4d(sb + j * OZ_B_PLANE, &mapB, fb, kt * OZ_BK, n0, j, bz);
+                const uint32_t sb = sa + (uint32_t)s * OZ_IMG;
+                bulk_load(sa, ga + (long long)kt * s * OZ_IMG, (uint32_t)(s * OZ_IMG), fb);
+                const int8_t* gbk = gb + (long long)kt * s * OZ_IMG;
+                for (int j = 0; j < s; ++j) bulk_load(sb + j * OZ_B_PLANE, gbk + j * OZ_IMG, OZ_B_PLANE, fb);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        const uint32_t idesc = umma_idesc_i8(OZ_BM, OZ_BN);
         for (int ch = 0; ch < nchunks; ++ch) {
             if (ch > 0) {   // accumulators must have been drained by the epilogue warps
                 mbar_wait_(smem_u32(&acc_empty), (ch - 1) & 1);
@@ -200,14 +218,14 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint32_t sa = smem0 + (uint32_t)st * stage_bytes;
-                    const uint32_t sb = sa + (uint32_t)s * OZ_A_PLANE;
+                    const uint32_t sb = sa + (uint32_t)s * OZ_IMG;
                     // Plane A_i meets B_0 .. B_{s-1-i}; their products belong to the accumulators of the
                     // diagonals g = i .. s-1, which are CONSECUTIVE 64-column blocks of TMEM, and the B planes
                     // are consecutive 64-row blocks of shared memory.  So all pairs of one i are a single
                     // wide MMA (N = 64 (s-i), split at the instruction limit N = 256): A_i is read from shared
                     // memory once instead of s-i times -- the N = 64 form is shared-memory-bandwidth bound.
                     for (int i = 0; i < s; ++i) {
-                        const uint64_t da = umma_desc_sw32(sa + i * OZ_A_PLANE);
+                        const uint64_t da = umma_desc_sw32(sa + i * OZ_IMG);
                         const int nplanes = s - i;
                         const uint32_t accum = (kt > kt0 || i > 0) ? 1u : 0u;   // i = 0 touches every accumulator
                         const int np1 = nplanes < 4 ? nplanes : 4;
@@ -273,9 +291,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------------------
-// slicing: FP64 -> s signed 8-bit planes, K-contiguous, with per-row power-of-two scaling
+// slicing: FP64 -> s signed 8-bit planes in tile-image order, per-row power-of-two scaling
 //   KC operand: element (x, k) at P[x*ld + k]   ;   MC operand: element (x, k) at P[k*ld + x]
-// planes[i][x][k] (x < X, k < K),  ex[x] = exponent with |P(x,:)| * 2^-ex < 1
+// ex[x] = exponent with |P(x,:)| * 2^-ex < 1
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int exp_for(double amax) {
     if (!(amax > 0.0)) return 0;
@@ -284,15 +302,31 @@ __device__ __forceinline__ int exp_for(double amax) {
     return e;
 }
 
+// 4 consecutive k (k4 % 4 == 0) of row x: one 32-bit store per plane
+__device__ __forceinline__ void slice4_store(double (&v)[4], int x, int k4, int s, int nkt, int8_t* planes) {
+    int8_t* dst = planes + img_offset(x, k4, 0, s, nkt);
+    for (int i = 0; i < s; ++i) {
+        uint32_t pack = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double t = v[u] * 128.0;
+            const double a = trunc(t);
+            v[u] = t - a;
+            pack |= ((uint32_t)(uint8_t)(int8_t)(int)a) << (8 * u);
+        }
+        *reinterpret_cast<uint32_t*>(dst + (long long)i * OZ_IMG) = pack;
+    }
+}
+
 // one CTA per row (KC): coalesced along k
 __global__ void __launch_bounds__(256) slice_kc_kernel(const double* __restrict__ Pb, long long ld, long long sP,
                                                        int X, int K, int s, int8_t* __restrict__ planes_b,
-                                                       int* __restrict__ ex_b) {
+                                                       long long sPl, int* __restrict__ ex_b) {
     __shared__ double red[8];
     __shared__ int e_sh;
     const int x = blockIdx.x;
     const double* P = Pb + (long long)blockIdx.z * sP;
-    int8_t* planes = planes_b + (long long)blockIdx.z * s * X * K;
+    int8_t* planes = planes_b + (long long)blockIdx.z * sPl;
     int* ex = ex_b + (long long)blockIdx.z * X;
     const double* row = P + (long long)x * ld;
     double amax = 0.0;
@@ -309,23 +343,12 @@ __global__ void __launch_bounds__(256) slice_kc_kernel(const double* __restrict_
     }
     __syncthreads();
     const int e = e_sh;
-    const long long plane_stride = (long long)X * K;
-    // 4 consecutive k per thread -> one 32-bit store per plane
+    const int nkt = K / OZ_BK;
     for (int k4 = threadIdx.x * 4; k4 < K; k4 += 1024) {
         double v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) v[u] = scalbn(row[k4 + u], -e);
-        for (int i = 0; i < s; ++i) {
-            uint32_t pack = 0;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const double t = v[u] * 128.0;
-                const double a = trunc(t);
-                v[u] = t - a;
-                pack |= ((uint32_t)(uint8_t)(int8_t)(int)a) << (8 * u);
-            }
-            *reinterpret_cast<uint32_t*>(planes + i * plane_stride + (long long)x * K + k4) = pack;
-        }
+        slice4_store(v, x, k4, s, nkt, planes);
     }
 }
 
@@ -360,10 +383,10 @@ __global__ void __launch_bounds__(256) absmax_mc_kernel(const double* __restrict
 // MC operand, pass 2: 32(k) x 32(x) tiles transposed through shared memory
 __global__ void __launch_bounds__(256) slice_mc_kernel(const double* __restrict__ Pb, long long ld, long long sP,
                                                        int X, int K, int s, int8_t* __restrict__ planes_b,
-                                                       const int* __restrict__ ex_b) {
+                                                       long long sPl, const int* __restrict__ ex_b) {
     __shared__ double tile[32][33];
     const double* P = Pb + (long long)blockIdx.z * sP;
-    int8_t* planes = planes_b + (long long)blockIdx.z * s * X * K;
+    int8_t* planes = planes_b + (long long)blockIdx.z * sPl;
     const int* ex = ex_b + (long long)blockIdx.z * X;
     const int x0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows of 32
@@ -375,54 +398,15 @@ __global__ void __launch_bounds__(256) slice_mc_kernel(const double* __restrict_
     double v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) v[u] = scalbn(tile[kl + u][xl], -e);
-    const long long plane_stride = (long long)X * K;
-    for (int i = 0; i < s; ++i) {
-        uint32_t pack = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const double t = v[u] * 128.0;
-            const double a = trunc(t);
-            v[u] = t - a;
-            pack |= ((uint32_t)(uint8_t)(int8_t)(int)a) << (8 * u);
-        }
-        *reinterpret_cast<uint32_t*>(planes + i * plane_stride + (long long)(x0 + xl) * K + k0 + kl) = pack;
-    }
+    slice4_store(v, x0 + xl, k0 + kl, s, K / OZ_BK, planes);
 }
 
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn g_encode = nullptr;
-
-static int get_encode() {
-    if (g_encode) return PLMC_OK;
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
-        return PLMC_ERR_LAUNCH;
-    g_encode = (EncodeTiledFn)fn;
-    return PLMC_OK;
-}
-
-// planes [batch][s][X][K] int8 -> 4-D map, box {32 B, box_rows, 1, 1}, SWIZZLE_32B
-static int make_plane_map(CUtensorMap* map, const int8_t* planes, int X, int K, int s, int batch, int box_rows) {
-    const cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)X, (cuuint64_t)s, (cuuint64_t)batch};
-    const cuuint64_t strides[3] = {(cuuint64_t)K, (cuuint64_t)K * (cuuint64_t)X,
-                                   (cuuint64_t)K * (cuuint64_t)X * (cuuint64_t)s};
-    const cuuint32_t box[4] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, 1, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void*)planes, dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? PLMC_OK : PLMC_ERR_LAUNCH;
-}
-
 static bool g_oz_attr = false;
 
-// scratch for ONE batch member (planes of both operands + exponents)
+// scratch for ONE batch member (tile images of both operands + exponents)
 long long ozaki_ws_bytes(int M, int N, int K, int s, bool same_operand) {
     const long long a = (long long)s * M * K, b = same_operand ? 0 : (long long)s * N * K;
     const long long pad = 1024;
@@ -434,17 +418,16 @@ long long ozaki_ws_bytes(int M, int N, int K, int s, bool same_operand) {
 int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA, const double* B, long long ldb,
                long long sB, double* C, long long ldc, long long sC, int M, int N, int K, double alpha, double beta,
                int lower, int s, bool same_operand, int batch, void* ws, long long ws_bytes, cudaStream_t st) {
-    if (s < 1 || s > OZ_SMAX || (M % OZ_BM) || (N % OZ_BN) || (K % 32) || batch < 1) return PLMC_ERR_BADARG;
+    if (s < 1 || s > OZ_SMAX || (M % OZ_BM) || (N % OZ_BM) || (K % 32) || batch < 1) return PLMC_ERR_BADARG;
     if (same_operand && (M != N)) return PLMC_ERR_BADARG;
     const long long pad = 1024;
     uint8_t* w0 = (uint8_t*)(((uintptr_t)ws + pad - 1) / pad * pad);
     const long long avail = ws_bytes - (long long)(w0 - (uint8_t*)ws);
     const long long need1 = ozaki_ws_bytes(M, N, K, s, same_operand);
     if (avail < need1) return PLMC_ERR_BADARG;
-    if (get_encode()) return PLMC_ERR_LAUNCH;
     const int bc_max = (int)((avail / need1) < batch ? (avail / need1) : batch);
-    const long long bytesA = (((long long)s * M * K + pad - 1) / pad) * pad;
-    const long long bytesB = same_operand ? 0 : (((long long)s * N * K + pad - 1) / pad) * pad;
+    const long long bytesA = (long long)s * M * K;                       // multiple of 4096
+    const long long bytesB = same_operand ? 0 : (long long)s * N * K;
     if (!g_oz_attr) {
         if (cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  OZ_STAGES * oz_stage_bytes(OZ_SMAX) + 1024) != cudaSuccess)
@@ -455,32 +438,31 @@ int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA,
 
     for (int b0 = 0; b0 < batch; b0 += bc_max) {
         const int bc = (batch - b0) < bc_max ? (batch - b0) : bc_max;
-        // layout of the scratch for this pass: A planes [bc][s][M][K] | B planes [bc][s][N][K] | ea [bc][M] | eb [bc][N]
-        // (member planes are contiguous: the per-member byte counts are NOT padded inside the 4-D maps)
+        // scratch of this pass: A images [bc][...] | B images [bc][...] | ea [bc][M] | eb [bc][N]
         int8_t* pa = (int8_t*)w0;
         int8_t* pb = same_operand ? pa : (int8_t*)(w0 + bytesA * bc);
         int* ea = (int*)(w0 + (bytesA + bytesB) * bc);
         int* eb = same_operand ? ea : ea + (long long)bc * M;
-        auto slice = [&](bool kc, const double* P, long long ld, long long sP, int X, int8_t* planes, int* ex) {
+        auto slice = [&](bool kc, const double* P, long long ld, long long sP, int X, int8_t* planes,
+                         long long sPl, int* ex) {
             if (kc) {
-                slice_kc_kernel<<<dim3(X, 1, bc), 256, 0, st>>>(P, ld, sP, X, K, s, planes, ex);
+                slice_kc_kernel<<<dim3(X, 1, bc), 256, 0, st>>>(P, ld, sP, X, K, s, planes, sPl, ex);
             } else {
                 cudaMemsetAsync(ex, 0x80, sizeof(int) * (size_t)X * bc, st);
                 absmax_mc_kernel<<<dim3((X + 63) / 64, (K + 255) / 256, bc), 256, 0, st>>>(P, ld, sP, X, K, ex);
-                slice_mc_kernel<<<dim3(X / 32, K / 32, bc), 256, 0, st>>>(P, ld, sP, X, K, s, planes, ex);
+                slice_mc_kernel<<<dim3(X / 32, K / 32, bc), 256, 0, st>>>(P, ld, sP, X, K, s, planes, sPl, ex);
             }
         };
-        slice(aKC, A + (long long)b0 * sA, lda, sA, M, pa, ea);
-        if (!same_operand) slice(bKC, B + (long long)b0 * sB, ldb, sB, N, pb, eb);
+        slice(aKC, A + (long long)b0 * sA, lda, sA, M, pa, bytesA, ea);
+        if (!same_operand) slice(bKC, B + (long long)b0 * sB, ldb, sB, N, pb, bytesB, eb);
         PLMC_CHECK_LAUNCH();
-        CUtensorMap mapA, mapB;
-        if (make_plane_map(&mapA, pa, M, K, s, bc, OZ_BM) || make_plane_map(&mapB, pb, N, K, s, bc, OZ_BN))
-            return PLMC_ERR_LAUNCH;
         OzArgs p;
-        p.C = C + (long long)b0 * sC; p.ldc = ldc; p.sC = sC; p.ea = ea; p.eb = eb;
+        p.C = C + (long long)b0 * sC; p.ldc = ldc; p.sC = sC;
+        p.PA = pa; p.PB = pb; p.sPA = bytesA; p.sPB = same_operand ? bytesA : bytesB;
+        p.ea = ea; p.eb = eb;
         p.M = M; p.N = N; p.K = K; p.s = s;
         p.alpha = alpha; p.beta = beta; p.lower = lower;
-        ozaki_gemm_kernel<<<dim3((unsigned)((N / OZ_BN) * (M / OZ_BM)), 1, bc), OZ_THREADS, smem, st>>>(mapA, mapB, p);
+        ozaki_gemm_kernel<<<dim3((unsigned)((N / OZ_BN) * (M / OZ_BM)), 1, bc), OZ_THREADS, smem, st>>>(p);
         PLMC_CHECK_LAUNCH();
         note_launch(3);
     }

@@ -38,10 +38,10 @@ def check(layout, M, N, K, s, kind="rand", alpha=1.0, beta=0.0, lower=False, sam
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "bringup"
 if mode == "bringup":
-    check(0, 128, 64, 32, 1, "int")
-    check(0, 128, 64, 64, 1, "int")
+    check(0, 128, 128, 32, 1, "int")
+    check(0, 128, 128, 64, 1, "int")
     check(0, 256, 128, 512, 1, "int")
-    check(0, 128, 64, 32, 2, "rand")
+    check(0, 128, 128, 32, 2, "rand")
     check(0, 256, 128, 256, 7, "rand")
     for layout in range(4):
         check(layout, 384, 256, 640, 7, "rand", alpha=-1.0, beta=1.0)
