@@ -136,7 +136,7 @@ int plmc_gemm(int layout, const double* A, long long lda, long long sA, const do
               int triA, int triB, int batch, void* stream);
 
 /* ---- FP64 GEMM on the tcgen05 INT8 tensor path (Ozaki splitting; csrc/ozaki.cu):
- * C = alpha op(A) op(B) + beta C for ONE matrix, beta in {0,1}, M%128==0, N%64==0, K%32==0.
+ * C = alpha op(A) op(B) + beta C for ONE matrix, M%128==0, N%128==0, K%32==0.
  * `slices` (1..7) signed 8-bit planes of 7 bits per operand -> 7*slices mantissa bits relative
  * to the largest entry of each row of op(A) / column of op(B).  same_operand != 0: op(B)^T is
  * op(A) (SYRK), sliced once.  ws: plmc_ozaki_ws_bytes(...) bytes of scratch.                  */

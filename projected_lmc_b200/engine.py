@@ -59,7 +59,7 @@ class LatentEngine:
     # GEMM dimension routed to the INT8 path.  Defaults come from the environment so that the
     # whole test-suite can be run in either mode.
     fp64_slices = int(__import__("os").environ.get("PLMC_FP64_SLICES", "7"))
-    fp64_min_dim = int(__import__("os").environ.get("PLMC_FP64_MIN_DIM", "1024"))
+    fp64_min_dim = int(__import__("os").environ.get("PLMC_FP64_MIN_DIM", "512"))
     _oz = None
 
     def _configure_fp64(self, device, np_, q=1):
