@@ -137,9 +137,10 @@ int plmc_gemm(int layout, const double* A, long long lda, long long sA, const do
 
 /* ---- FP64 GEMM on the tcgen05 INT8 tensor path (Ozaki splitting; csrc/ozaki.cu):
  * C = alpha op(A) op(B) + beta C for ONE matrix, M%128==0, N%128==0, K%32==0.
- * `slices` (1..7) signed 8-bit planes of 7 bits per operand -> 7*slices mantissa bits relative
- * to the largest entry of each row of op(A) / column of op(B).  same_operand != 0: op(B)^T is
- * op(A) (SYRK), sliced once.  ws: plmc_ozaki_ws_bytes(...) bytes of scratch.                  */
+ * `slices` (1..7) signed 8-bit planes (balanced base-256 digits) per operand -> 8*slices-1
+ * mantissa bits relative to the largest entry of each row of op(A) / column of op(B); 7 slices
+ * reproduce a DGEMM to its own rounding level.  same_operand != 0: op(B)^T is op(A) (SYRK),
+ * sliced once.  ws: plmc_ozaki_ws_bytes(...) bytes of scratch.                                */
 long long plmc_ozaki_ws_bytes(int M, int N, int K, int slices, int same_operand);
 /* Route every GEMM of the blocked factorisation layer (potrf / trsm / trtri / lauum) whose M, N
  * and K are all >= min_dim through the INT8 path with `slices` planes, using the caller-owned

@@ -7,10 +7,13 @@
 // tensor path is two orders of magnitude wider, so a product of two FP64 matrices
 // split into s planes of 7 bits costs s(s+1)/2 INT8 GEMMs and still wins.
 //
-//   x = A[m,k] * 2^-ea[m]  (|x| < 1),  a_i = trunc(x * 2^7), x <- x * 2^7 - a_i   (i < s, exact)
-//   A[m,k] = 2^ea[m] * sum_i a_i 2^-7(i+1) + O(2^-7s)        (same for columns of B)
-//   C[m,n] += alpha * 2^(ea[m]+eb[n]-14) * sum_{g<s} 2^-7g * D_g[m,n],
+//   x = A[m,k] * 2^-(ea[m]+1)  (|x| < 1/2),  Q = rint(x * 2^(8s-1))  (a 64-bit integer, exact up to the rounding)
+//   Q = sum_i a_i 256^(s-1-i) with BALANCED base-256 digits a_i in [-128, 127] (a_0 in [-65, 65]):
+//   A[m,k] = 2^(ea[m]+1) * sum_i a_i 2^-(7+8i) + O(2^-8s)     (same for columns of B)
+//   C[m,n] += alpha * 2^(ea[m]+eb[n]-12) * sum_{g<s} 2^-8g * D_g[m,n],
 //   D_g = sum_{i+j=g} A_i B_j^T   (INT32, exact for K-chunks <= 16384)
+// Balanced digits use all 8 bits of a signed plane, so s planes carry 8s-1 bits (s = 6: 47 bits) where
+// the usual sign-magnitude truncation carries 7s.
 //
 // Data layout ("tile images"): the slicers write the planes of an operand directly in the
 // order and byte pattern the tensor core wants in shared memory:
@@ -35,7 +38,7 @@ constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 32;   // BK in int8 elements = by
 constexpr int OZ_SMAX = 7;                           // TMEM: 7 accumulators x 64 columns = 448 <= 512
 constexpr int OZ_STAGES = 5;
 constexpr int OZ_THREADS = 192;                      // warp0 producer, warp1 MMA + TMEM alloc, warps 2..5 epilogue
-constexpr int OZ_KCHUNK = 16384;                     // INT32 exactness: 7 * 16384 * 127^2 < 2^31
+constexpr int OZ_KCHUNK = 16384;                     // INT32 exactness: 7 * 16384 * 128^2 < 2^31
 constexpr int OZ_IMG = OZ_BM * OZ_BK;                // 4096 B: one plane of one (128-row, 32-k) tile
 constexpr int OZ_B_PLANE = OZ_BN * OZ_BK;            // 2048 B: half an image
 
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzArgs 
         // ===== epilogue: TMEM -> registers -> FP64 recombination -> C =====
         const int quad = warp & 3;                 // TMEM lane quarter this warp may access
         const int row = m0 + quad * 32 + lane;
-        const double sa = scalbn(1.0, max(p.ea[(long long)bz * p.M + row], -1022) - 14);
+        const double sa = scalbn(1.0, max(p.ea[(long long)bz * p.M + row], -1022) - 12);
         const int* ebz = p.eb + (long long)bz * p.N;
         double* crow = p.C + (long long)bz * p.sC + (long long)row * p.ldc + n0;
         for (int ch = 0; ch < nchunks; ++ch) {
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzArgs 
                     tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(gI * OZ_BN + c0), r);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fma(v[j], 0.0078125, (double)(int)r[j]);
+                    for (int j = 0; j < 16; ++j) v[j] = fma(v[j], 0.00390625, (double)(int)r[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < 16; j += 2) {
@@ -299,20 +302,24 @@ __device__ __forceinline__ int exp_for(double amax) {
     if (!(amax > 0.0)) return 0;
     int e;
     frexp(amax, &e);     // amax = f * 2^e, f in [0.5, 1)  ->  amax * 2^-e < 1
-    return e;
+    return max(e, -1022);
 }
 
-// 4 consecutive k (k4 % 4 == 0) of row x: one 32-bit store per plane
-__device__ __forceinline__ void slice4_store(double (&v)[4], int x, int k4, int s, int nkt, int8_t* planes) {
+// 4 consecutive k (k4 % 4 == 0) of row x with row exponent e (|v| * 2^-e < 1): one 32-bit store per plane.
+// Balanced base-256 digits of Q = rint(v * 2^(8s-2-e)), least significant first.
+__device__ __forceinline__ void slice4_store(const double (&v)[4], int e, int x, int k4, int s, int nkt,
+                                             int8_t* planes) {
     int8_t* dst = planes + img_offset(x, k4, 0, s, nkt);
-    for (int i = 0; i < s; ++i) {
+    long long Q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Q[u] = __double2ll_rn(scalbn(v[u], 8 * s - 2 - e));
+    for (int i = s - 1; i >= 0; --i) {
         uint32_t pack = 0;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const double t = v[u] * 128.0;
-            const double a = trunc(t);
-            v[u] = t - a;
-            pack |= ((uint32_t)(uint8_t)(int8_t)(int)a) << (8 * u);
+            const int d = (i > 0) ? (int)((Q[u] + 128) & 255) - 128 : (int)Q[u];
+            Q[u] = (Q[u] - d) >> 8;
+            pack |= ((uint32_t)(uint8_t)(int8_t)d) << (8 * u);
         }
         *reinterpret_cast<uint32_t*>(dst + (long long)i * OZ_IMG) = pack;
     }
@@ -347,8 +354,8 @@ __global__ void __launch_bounds__(256) slice_kc_kernel(const double* __restrict_
     for (int k4 = threadIdx.x * 4; k4 < K; k4 += 1024) {
         double v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = scalbn(row[k4 + u], -e);
-        slice4_store(v, x, k4, s, nkt, planes);
+        for (int u = 0; u < 4; ++u) v[u] = row[k4 + u];
+        slice4_store(v, e, x, k4, s, nkt, planes);
     }
 }
 
@@ -397,8 +404,8 @@ __global__ void __launch_bounds__(256) slice_mc_kernel(const double* __restrict_
     const int e = max(ex[x0 + xl], -1022);   // all-zero column: any exponent works
     double v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = scalbn(tile[kl + u][xl], -e);
-    slice4_store(v, x0 + xl, k0 + kl, s, K / OZ_BK, planes);
+    for (int u = 0; u < 4; ++u) v[u] = tile[kl + u][xl];
+    slice4_store(v, e, x0 + xl, k0 + kl, s, K / OZ_BK, planes);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -33,14 +33,15 @@ def test_ozaki_gemm_layouts(layout, alpha, beta):
     C = C0.clone()
     ref = alpha * (A.T if a_mc else A) @ (B if b_nc else B.T) + beta * C0
     ops.ozaki_gemm(layout, A, B, C, M, N, K, alpha=alpha, beta=beta, slices=7)
-    assert (C - ref).abs().max().item() < 1e-12 * ref.abs().max().item() * 5
+    assert (C - ref).abs().max().item() < 5e-14 * ref.abs().max().item()
 
 
 def test_single_plane_inputs_are_exact():
     M, N, K = 256, 128, 512
     g = torch.Generator().manual_seed(0)
-    A = (torch.randint(-127, 128, (M, K), generator=g).double() / 128.0).to(DEV)
-    B = (torch.randint(-127, 128, (N, K), generator=g).double() / 128.0).to(DEV)
+    # |x| * 2^-(e+1) < 1/2 and 7 bits in the leading plane: integers / 64 up to 63 fit one plane exactly
+    A = (torch.randint(-63, 64, (M, K), generator=g).double() / 64.0).to(DEV)
+    B = (torch.randint(-63, 64, (N, K), generator=g).double() / 64.0).to(DEV)
     C = torch.empty(M, N, dtype=torch.float64, device=DEV)
     ops.ozaki_gemm(0, A, B, C, M, N, K, slices=1)
     assert torch.equal(C, A @ B.T)
@@ -56,7 +57,7 @@ def test_rows_with_very_different_scales_and_zero_rows():
     ops.ozaki_gemm(0, A, B, C, M, N, K, slices=7)
     ref = A @ B.T
     scale = A.abs().max(1).values[:, None] * B.abs().max(1).values[None, :] * K ** 0.5 + 1e-300
-    assert ((C - ref).abs() / scale).max().item() < 1e-13
+    assert ((C - ref).abs() / scale).max().item() < 1e-14
     assert C[7].abs().max().item() == 0.0
 
 
@@ -73,10 +74,10 @@ def test_syrk_lower_same_operand_and_k_chunks():
             if 64 * tj > 128 * ti + 127:
                 assert torch.equal(C[blk], C0[blk])                       # above the diagonal: untouched
             else:
-                assert (C[blk] - ref[blk]).abs().max().item() < 1e-12 * ref.abs().max().item()
+                assert (C[blk] - ref[blk]).abs().max().item() < 5e-14 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("slices,tol", [(5, 1e-8), (6, 1e-10), (7, 1e-12)])
+@pytest.mark.parametrize("slices,tol", [(4, 2e-7), (5, 1e-9), (6, 5e-12), (7, 3e-14)])   # 8s - 1 bits
 def test_accuracy_scales_with_slices(slices, tol):
     n = 512
     A, B = rnd(n, 1024, seed=8), rnd(n, 1024, seed=9)
