@@ -40,6 +40,10 @@ int plmc_init(void);
  * tiles actually computed).  Outputs are HOST pointers (may be NULL).            */
 int plmc_stats_reset(void);
 int plmc_stats_get(long long* launches_host, long long* gemm_launches_host, double* gemm_flops_host);
+/* diagnostics: with tracing on, every GEMM of the factorisation layer is bracketed by CUDA events;
+ * plmc_trace_report synchronises the device and prints time and FLOP rate per GEMM shape to stderr. */
+int plmc_trace_enable(int on);
+int plmc_trace_report(void);
 /* npad for a problem of order n (multiple of 128) */
 long long plmc_npad(long long n);
 /* bytes of the Dinv side buffer potrf needs for `batch` matrices of order npad */
@@ -147,6 +151,10 @@ long long plmc_ozaki_ws_bytes(int M, int N, int K, int slices, int same_operand)
  * scratch `ws` (a GEMM whose planes do not fit falls back to the DMMA kernel).  slices = 0
  * switches the emulation off (pure FP64 DMMA arithmetic).  Process-wide setting.              */
 int plmc_set_fp64_emulation(void* ws, long long ws_bytes, int slices, int min_dim);
+/* diagnostics: with a device buffer of 64 x 8 int64 set, CTA 0 of every later INT8 GEMM launch records
+ * clock64 stamps per tile (0 MMA start, 1 last MMA issued, 2 accumulators complete, 3 TMEM drained,
+ * 4 C written, 5/6 first/last copy issued); NULL switches it off.                                  */
+int plmc_ozaki_debug(long long* stamps);
 int plmc_ozaki_gemm(int layout, const double* A, long long lda, const double* B, long long ldb, double* C,
                     long long ldc, int M, int N, int K, double alpha, double beta, int lower, int slices,
                     int same_operand, void* ws, long long ws_bytes, void* stream);

@@ -23,6 +23,9 @@ _SIGNATURES = {
     "plmc_version": [],
     "plmc_init": [],
     "plmc_stats_reset": [],
+    "plmc_trace_enable": [I],
+    "plmc_ozaki_debug": [P],
+    "plmc_trace_report": [],
     "plmc_stats_get": [P, P, P],
     "plmc_npad": [LL],
     "plmc_dinv_bytes": [LL, I],

@@ -84,6 +84,15 @@ int plmc_set_fp64_emulation(void* ws, long long ws_bytes, int slices, int min_di
     return PLMC_OK;
 }
 
+int plmc_trace_enable(int on) {
+    trace_enable(on != 0);
+    return PLMC_OK;
+}
+int plmc_trace_report(void) {
+    trace_report();
+    return PLMC_OK;
+}
+
 int plmc_init(void) { return gemm_init_attrs(); }
 
 int plmc_stats_reset(void) {

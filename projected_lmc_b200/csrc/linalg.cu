@@ -1,6 +1,11 @@
 #include "linalg.cuh"
 #include "potrf_leaf.cuh"
 
+#include <array>
+#include <cstdio>
+#include <map>
+#include <vector>
+
 namespace plmc {
 
 // copy Dinv leaves over the diagonal blocks (lower part) : final step of trtri
@@ -31,8 +36,51 @@ static int leaf_attr() {
 // ---------------------------------------------------------------------------
 static inline int split128(int n) { return ((n / LEAF) / 2) * LEAF; }
 
+// ---- optional per-shape timing of every GEMM of the recursion (plmc_trace_enable / plmc_trace_report):
+// CUDA events around each launch, aggregated by (path, M, N, K, lower, batch) at report time.
+struct TraceRec { int path, M, N, K, lower, batch; cudaEvent_t e0, e1; };
+static bool g_trace = false;
+static std::vector<TraceRec> g_trace_recs;
+
+static void gemm_impl(LaCtx& cx, bool aKC, bool bKC, BMat A, BMat B, BMat C, int M, int N, int K, double alpha,
+                      double beta, int lower, int triA, int triB, int* path);
+
 static void gemm(LaCtx& cx, bool aKC, bool bKC, BMat A, BMat B, BMat C, int M, int N, int K, double alpha,
                  double beta, int lower = 0, int triA = 0, int triB = 0) {
+    int path = 0;
+    if (!g_trace) { gemm_impl(cx, aKC, bKC, A, B, C, M, N, K, alpha, beta, lower, triA, triB, &path); return; }
+    TraceRec r{0, M, N, K, lower, cx.batch, nullptr, nullptr};
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, cx.st);
+    gemm_impl(cx, aKC, bKC, A, B, C, M, N, K, alpha, beta, lower, triA, triB, &r.path);
+    cudaEventRecord(r.e1, cx.st);
+    g_trace_recs.push_back(r);
+}
+
+void trace_enable(bool on) { g_trace = on; }
+
+void trace_report() {
+    cudaDeviceSynchronize();
+    struct Agg { long long count = 0; double ms = 0, flop = 0; };
+    std::map<std::array<int, 6>, Agg> agg;
+    for (auto& r : g_trace_recs) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        Agg& a = agg[{r.path, r.M, r.N, r.K, r.lower, r.batch}];
+        a.count++; a.ms += ms;
+        a.flop += 2.0 * r.M * r.N * r.K * r.batch * (r.lower ? 0.5 : 1.0);
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    g_trace_recs.clear();
+    fprintf(stderr, "path      M      N      K lower batch   count   total_ms  TFLOP/s\n");
+    for (auto& kv : agg)
+        fprintf(stderr, "%-5s %6d %6d %6d %5d %5d %7lld %10.2f %8.1f\n", kv.first[0] ? "int8" : "dmma", kv.first[1],
+                kv.first[2], kv.first[3], kv.first[4], kv.first[5], kv.second.count, kv.second.ms,
+                kv.second.flop / kv.second.ms / 1e9);
+}
+
+static void gemm_impl(LaCtx& cx, bool aKC, bool bKC, BMat A, BMat B, BMat C, int M, int N, int K, double alpha,
+                      double beta, int lower, int triA, int triB, int* path) {
     if (cx.status) return;
     if (cx.oz_slices > 0 && !triA && !triB && M >= cx.oz_min && N >= cx.oz_min && K >= cx.oz_min) {
         // large update: FP64 product through the INT8 tensor path (all batch members per launch when
@@ -41,6 +89,7 @@ static void gemm(LaCtx& cx, bool aKC, bool bKC, BMat A, BMat B, BMat C, int M, i
         if (ozaki_ws_bytes(M, N, K, cx.oz_slices, same) + 1024 <= cx.oz_bytes) {
             cx.status = ozaki_gemm(aKC, bKC, A.p, A.ld, A.stride, B.p, B.ld, B.stride, C.p, C.ld, C.stride, M, N, K,
                                    alpha, beta, lower, cx.oz_slices, same, cx.batch, cx.oz_ws, cx.oz_bytes, cx.st);
+            *path = 1;
             return;
         }
     }

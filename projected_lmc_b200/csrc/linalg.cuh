@@ -30,6 +30,9 @@ struct LaCtx {
     int oz_min = 1024;  // smallest M, N, K routed to the INT8 path
 };
 
+void trace_enable(bool on);
+void trace_report();
+
 long long ozaki_ws_bytes(int M, int N, int K, int s, bool same_operand);
 int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA, const double* B, long long ldb,
                long long sB, double* C, long long ldc, long long sC, int M, int N, int K, double alpha, double beta,

@@ -25,8 +25,8 @@
 // first version used 4-D TMA tensor maps with 32-byte inner boxes and was bound by the
 // L1TEX->XBAR request rate, ncu: l1tex__m_l1tex2xbar_req_cycles_active 83 %.)
 //
-// Kernel: one CTA per 128 x 64 output tile; warp 0 = copy producer, warp 1 = MMA issuer
-// (one elected thread), warps 2..5 = epilogue.  s accumulators (one per diagonal g, 64
+// Kernel: persistent, one CTA per SM walking 128 x 64 output tiles; warp 0 = copy producer (runs ahead
+// into the next tile), warp 1 = MMA issuer (one elected thread), warps 2..5 = epilogue.  s accumulators (one per diagonal g, 64
 // TMEM columns each, 448 of 512 columns at s = 7).  All pairs (i, j) of one A plane i are a
 // single wide MMA: their accumulators g = i..s-1 are consecutive TMEM column blocks and the
 // B planes consecutive shared-memory row blocks, so A_i is read from shared memory once.
@@ -36,13 +36,16 @@ namespace plmc {
 
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 32;   // BK in int8 elements = bytes
 constexpr int OZ_SMAX = 7;                           // TMEM: 7 accumulators x 64 columns = 448 <= 512
-constexpr int OZ_STAGES = 5;
+constexpr int OZ_STAGES = 5;                         // ring depth (4 at s = 7: 227 KB of shared memory per CTA)
+constexpr int OZ_STG_BYTES = 4 * 4096;               // epilogue staging: one 32 x 16 FP64 block per epilogue warp
 constexpr int OZ_THREADS = 192;                      // warp0 producer, warp1 MMA + TMEM alloc, warps 2..5 epilogue
 constexpr int OZ_KCHUNK = 16384;                     // INT32 exactness: 7 * 16384 * 128^2 < 2^31
 constexpr int OZ_IMG = OZ_BM * OZ_BK;                // 4096 B: one plane of one (128-row, 32-k) tile
 constexpr int OZ_B_PLANE = OZ_BN * OZ_BK;            // 2048 B: half an image
 
 __host__ __device__ inline int oz_stage_bytes(int s) { return s * (OZ_IMG + OZ_B_PLANE); }
+__host__ __device__ inline int oz_stages(int s) { return s >= 7 ? 4 : OZ_STAGES; }
+__host__ __device__ inline int oz_smem_bytes(int s) { return oz_stages(s) * oz_stage_bytes(s) + OZ_STG_BYTES + 1024; }
 
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -117,6 +120,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+// exact int32 -> double without the (slow) I2F.F64 pipe: 2^52 + 2^31 + r is representable, subtract the bias
+__device__ __forceinline__ double i32_to_f64(uint32_t r) {
+    return __hiloint2double(0x43300000, (int)(r ^ 0x80000000u)) - 4503601774854144.0;
+}
+
 // byte offset of element (x, k) of plane i inside the tile-image layout of one batch member
 __device__ __forceinline__ long long img_offset(int x, int k, int i, int s, int nkt) {
     const int tile = x >> 7, r = x & 127, kt = k >> 5, kk = k & 31;
@@ -136,36 +150,57 @@ struct OzArgs {
     int s;                  // planes (1..7)
     double alpha;
     double beta;            // C = alpha * A B + beta * C   (C is not read when beta == 0)
-    int lower;              // skip tiles entirely above the diagonal (C origin on the diagonal)
+    int lower;              // M == N: only tiles that touch the lower triangle (C origin on the diagonal)
+    int per_member;         // output tiles of one batch member
+    int total;              // per_member * batch members of this launch
+    long long* dbg;         // diagnostics (plmc_ozaki_debug): clock64 stamps of CTA 0, 8 per tile, or NULL
 };
+#define OZ_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && nt < 64) p.dbg[nt * 8 + (slot)] = clock64(); } while (0)
 
+// work item w -> (batch member, 128-row block, 64-column block)
+struct OzTile { int bz, tm, tn; };
+__device__ __forceinline__ OzTile oz_decode(const OzArgs& p, int w) {
+    OzTile t;
+    t.bz = w / p.per_member;
+    const int idx = w - t.bz * p.per_member;
+    if (p.lower) {
+        // row block tm owns the 2 tm + 2 column blocks tn <= 2 tm + 1: idx in [tm (tm+1), (tm+1)(tm+2))
+        int tm = (int)((sqrtf(4.0f * (float)idx + 1.0f) - 1.0f) * 0.5f);
+        while (tm * (tm + 1) > idx) --tm;
+        while ((tm + 1) * (tm + 2) <= idx) ++tm;
+        t.tm = tm;
+        t.tn = idx - tm * (tm + 1);
+    } else {
+        // grouped raster: bands of 8 tile-rows walk the columns together, so the CTAs in flight share
+        // 8 A row-blocks and ~18 B column-blocks out of L2 instead of streaming all of B
+        const int tiles_m = p.M / OZ_BM, tiles_n = p.N / OZ_BN;
+        const int GROUP = 8;
+        const int per_group = GROUP * tiles_n;
+        const int gid = idx / per_group;
+        const int first = gid * GROUP;
+        const int gsz = min(tiles_m - first, GROUP);
+        const int rem = idx - gid * per_group;
+        t.tm = first + rem % gsz;
+        t.tn = rem / gsz;
+    }
+    return t;
+}
+
+// Persistent: one CTA per SM walks the work items blockIdx.x, blockIdx.x + gridDim.x, ... ; every item costs
+// the same (same K), so the static round-robin is balanced to one tile.  The copy ring, the accumulator
+// hand-over and TMEM live across items: the producer is already filling the ring for the next tile while
+// the epilogue warps drain the accumulators of the current one.
 __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzArgs p) {
     extern __shared__ __align__(1024) uint8_t oz_smem[];
     __shared__ __align__(8) unsigned long long full_bar[OZ_STAGES], empty_bar[OZ_STAGES], acc_full, acc_empty;
     __shared__ uint32_t tmem_base_sh;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bz = blockIdx.z;   // batch member
-    // grouped raster: bands of 8 tile-rows walk the columns together, so the ~148 CTAs in flight
-    // share 8 A row-blocks and ~18 B column-blocks out of L2 instead of streaming all of B
-    int tm, tn;
-    {
-        const int tiles_m = p.M / OZ_BM, tiles_n = p.N / OZ_BN;
-        const int GROUP = 8;
-        const int per_group = GROUP * tiles_n;
-        const int gid = blockIdx.x / per_group;
-        const int first = gid * GROUP;
-        const int gsz = min(tiles_m - first, GROUP);
-        const int rem = blockIdx.x - gid * per_group;
-        tm = first + rem % gsz;
-        tn = rem / gsz;
-    }
-    const int m0 = tm * OZ_BM, n0 = tn * OZ_BN;
-    if (p.lower && n0 > m0 + OZ_BM - 1) return;   // whole CTA exits before any barrier / allocation
-
     const int s = p.s;
     const int stage_bytes = oz_stage_bytes(s);
+    const int nst = oz_stages(s);
     const uint32_t smem0 = (smem_u32(oz_smem) + 1023u) & ~1023u;
+    uint8_t* stg_base = oz_smem + (smem0 - smem_u32(oz_smem)) + nst * stage_bytes;   // 16 KB after the ring
     const int nkt = p.K / OZ_BK;
     const int kt_per_chunk = OZ_KCHUNK / OZ_BK;
     const int nchunks = (nkt + kt_per_chunk - 1) / kt_per_chunk;
@@ -192,98 +227,148 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzArgs 
     if (warp == 0) {
         // ===== copy producer: one 28 KB bulk copy (all A planes) + s 2 KB copies (B planes) per stage =====
         if (elect_one()) {
-            const int8_t* ga = p.PA + (long long)bz * p.sPA + (long long)tm * nkt * s * OZ_IMG;
-            // the 64-row B tile tn is half (tn & 1) of the image rows of 128-row tile tn >> 1
-            const int8_t* gb = p.PB + (long long)bz * p.sPB + (long long)(tn >> 1) * nkt * s * OZ_IMG + (tn & 1) * OZ_B_PLANE;
-            for (int kt = 0; kt < nkt; ++kt) {
-                const int st = kt % OZ_STAGES, round = kt / OZ_STAGES;
-                if (round > 0) mbar_wait_(smem_u32(&empty_bar[st]), (round - 1) & 1);
-                const uint32_t fb = smem_u32(&full_bar[st]);
-                mbar_expect_tx_(fb, (uint32_t)stage_bytes);
-                const uint32_t sa = smem0 + (uint32_t)st * stage_bytes;
-                const uint32_t sb = sa + (uint32_t)s * OZ_IMG;
-                bulk_load(sa, ga + (long long)kt * s * OZ_IMG, (uint32_t)(s * OZ_IMG), fb);
-                const int8_t* gbk = gb + (long long)kt * s * OZ_IMG;
-                for (int j = 0; j < s; ++j) bulk_load(sb + j * OZ_B_PLANE, gbk + j * OZ_IMG, OZ_B_PLANE, fb);
+            int it = 0;   // k-steps issued so far (ring position across work items)
+            int nt = 0;
+            for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++nt) {
+                const OzTile t = oz_decode(p, w);
+                const int8_t* ga = p.PA + (long long)t.bz * p.sPA + (long long)t.tm * nkt * s * OZ_IMG;
+                // the 64-row B tile tn is half (tn & 1) of the image rows of 128-row tile tn >> 1
+                const int8_t* gb = p.PB + (long long)t.bz * p.sPB + (long long)(t.tn >> 1) * nkt * s * OZ_IMG +
+                                   (t.tn & 1) * OZ_B_PLANE;
+                for (int kt = 0; kt < nkt; ++kt, ++it) {
+                    const int st = it % nst, round = it / nst;
+                    if (round > 0) mbar_wait_(smem_u32(&empty_bar[st]), (round - 1) & 1);
+                    const uint32_t fb = smem_u32(&full_bar[st]);
+                    if (kt == 0) OZ_STAMP(5);
+                    if (kt == nkt - 1) OZ_STAMP(6);
+                    mbar_expect_tx_(fb, (uint32_t)stage_bytes);
+                    const uint32_t sa = smem0 + (uint32_t)st * stage_bytes;
+                    const uint32_t sb = sa + (uint32_t)s * OZ_IMG;
+                    bulk_load(sa, ga + (long long)kt * s * OZ_IMG, (uint32_t)(s * OZ_IMG), fb);
+                    const int8_t* gbk = gb + (long long)kt * s * OZ_IMG;
+                    for (int j = 0; j < s; ++j) bulk_load(sb + j * OZ_B_PLANE, gbk + j * OZ_IMG, OZ_B_PLANE, fb);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        for (int ch = 0; ch < nchunks; ++ch) {
-            if (ch > 0) {   // accumulators must have been drained by the epilogue warps
-                mbar_wait_(smem_u32(&acc_empty), (ch - 1) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            const int kt0 = ch * kt_per_chunk, kt1 = min(nkt, kt0 + kt_per_chunk);
-            for (int kt = kt0; kt < kt1; ++kt) {
-                const int st = kt % OZ_STAGES, round = kt / OZ_STAGES;
-                mbar_wait_(smem_u32(&full_bar[st]), round & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (elect_one()) {
-                    const uint32_t sa = smem0 + (uint32_t)st * stage_bytes;
-                    const uint32_t sb = sa + (uint32_t)s * OZ_IMG;
-                    // Plane A_i meets B_0 .. B_{s-1-i}; their products belong to the accumulators of the
-                    // diagonals g = i .. s-1, which are CONSECUTIVE 64-column blocks of TMEM, and the B planes
-                    // are consecutive 64-row blocks of shared memory.  So all pairs of one i are a single
-                    // wide MMA (N = 64 (s-i), split at the instruction limit N = 256): A_i is read from shared
-                    // memory once instead of s-i times -- the N = 64 form is shared-memory-bandwidth bound.
-                    for (int i = 0; i < s; ++i) {
-                        const uint64_t da = umma_desc_sw32(sa + i * OZ_IMG);
-                        const int nplanes = s - i;
-                        const uint32_t accum = (kt > kt0 || i > 0) ? 1u : 0u;   // i = 0 touches every accumulator
-                        const int np1 = nplanes < 4 ? nplanes : 4;
-                        umma_i8(tmem_base + (uint32_t)i * OZ_BN, da, umma_desc_sw32(sb),
-                                umma_idesc_i8(OZ_BM, OZ_BN * np1), accum);
-                        if (nplanes > 4)
-                            umma_i8(tmem_base + (uint32_t)(i + 4) * OZ_BN, da, umma_desc_sw32(sb + 4 * OZ_B_PLANE),
-                                    umma_idesc_i8(OZ_BM, OZ_BN * (nplanes - 4)), accum);
-                    }
-                    umma_commit(smem_u32(&empty_bar[st]));            // frees the smem stage when the MMAs retire
-                    if (kt == kt1 - 1) umma_commit(smem_u32(&acc_full));  // accumulators complete for this chunk
+        int it = 0, phase = 0;   // ring position; accumulation phases (one per work item and K-chunk) so far
+        int nt = 0;
+        for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++nt) {
+            for (int ch = 0; ch < nchunks; ++ch, ++phase) {
+                if (phase > 0) {   // accumulators must have been drained by the epilogue warps
+                    mbar_wait_(smem_u32(&acc_empty), (phase - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                __syncwarp();
+                if (lane == 0) OZ_STAMP(0);
+                const int kt0 = ch * kt_per_chunk, kt1 = min(nkt, kt0 + kt_per_chunk);
+                for (int kt = kt0; kt < kt1; ++kt, ++it) {
+                    const int st = it % nst, round = it / nst;
+                    mbar_wait_(smem_u32(&full_bar[st]), round & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint32_t sa = smem0 + (uint32_t)st * stage_bytes;
+                        const uint32_t sb = sa + (uint32_t)s * OZ_IMG;
+                        // Plane A_i meets B_0 .. B_{s-1-i}; their products belong to the accumulators of the
+                        // diagonals g = i .. s-1, which are CONSECUTIVE 64-column blocks of TMEM, and the B
+                        // planes are consecutive 64-row blocks of shared memory.  So all pairs of one i are a
+                        // single wide MMA (N = 64 (s-i), split at the instruction limit N = 256): A_i is read
+                        // from shared memory once instead of s-i times.
+                        for (int i = 0; i < s; ++i) {
+                            const uint64_t da = umma_desc_sw32(sa + i * OZ_IMG);
+                            const int nplanes = s - i;
+                            const uint32_t accum = (kt > kt0 || i > 0) ? 1u : 0u;   // i = 0 touches every accumulator
+                            const int np1 = nplanes < 4 ? nplanes : 4;
+                            umma_i8(tmem_base + (uint32_t)i * OZ_BN, da, umma_desc_sw32(sb),
+                                    umma_idesc_i8(OZ_BM, OZ_BN * np1), accum);
+                            if (nplanes > 4)
+                                umma_i8(tmem_base + (uint32_t)(i + 4) * OZ_BN, da, umma_desc_sw32(sb + 4 * OZ_B_PLANE),
+                                        umma_idesc_i8(OZ_BM, OZ_BN * (nplanes - 4)), accum);
+                        }
+                        umma_commit(smem_u32(&empty_bar[st]));            // frees the smem stage when the MMAs retire
+                        if (kt == kt1 - 1) {
+                            umma_commit(smem_u32(&acc_full));  // accumulators complete for this chunk
+                            OZ_STAMP(1);
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> FP64 recombination -> C =====
+        // ===== epilogue: TMEM -> registers -> FP64 recombination -> shared-memory transpose -> C =====
+        // A TMEM lane is an output ROW, so each thread recombines 16 columns of its own row; the 32 x 16
+        // block of the warp is then turned through a swizzled staging tile so that global loads (beta) and
+        // stores run along rows: 16 lanes x 8 B = one full 128-byte line per half warp.
         const int quad = warp & 3;                 // TMEM lane quarter this warp may access
-        const int row = m0 + quad * 32 + lane;
-        const double sa = scalbn(1.0, max(p.ea[(long long)bz * p.M + row], -1022) - 12);
-        const int* ebz = p.eb + (long long)bz * p.N;
-        double* crow = p.C + (long long)bz * p.sC + (long long)row * p.ldc + n0;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            mbar_wait_(smem_u32(&acc_full), ch & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const double beta = (ch > 0) ? 1.0 : p.beta;   // later K-chunks accumulate onto the first
-#pragma unroll 1
-            for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
-                double v[16];
+        double* stg = reinterpret_cast<double*>(stg_base + quad * 4096);
+        const int rsub = lane >> 4, col = lane & 15;
+        int phase = 0;
+        int nt = 0;
+        for (int w = blockIdx.x; w < p.total; w += gridDim.x, ++nt) {
+            const OzTile t = oz_decode(p, w);
+            const int m0 = t.tm * OZ_BM, n0 = t.tn * OZ_BN;
+            const int row = m0 + quad * 32 + lane;
+            const double sa = p.alpha * scalbn(1.0, max(p.ea[(long long)t.bz * p.M + row], -1022) - 12);
+            const int* ebz = p.eb + (long long)t.bz * p.N + n0;
+            double* cw = p.C + (long long)t.bz * p.sC + (long long)(m0 + quad * 32) * p.ldc + n0;
+            for (int ch = 0; ch < nchunks; ++ch, ++phase) {
+                mbar_wait_(smem_u32(&acc_full), phase & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (warp == 2 && lane == 0) OZ_STAMP(2);
+                const double beta = (ch > 0) ? 1.0 : p.beta;   // later K-chunks accumulate onto the first
+                // phase A: drain TMEM.  v[b][j] = sum_g 2^-8g D_g[row][8 b + j], all 64 columns of the row kept
+                // in registers, so the accumulators go back to the MMA warp after ~3 us and the read-modify-
+                // write of C below overlaps the next tile's main loop.
+                double v[OZ_BN / 8][8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0.0;
-                for (int gI = s - 1; gI >= 0; --gI) {
-                    uint32_t r[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(gI * OZ_BN + c0), r);
+                for (int b = 0; b < OZ_BN / 8; ++b) {
+                    uint32_t r[OZ_SMAX][8];
+#pragma unroll
+                    for (int gI = 0; gI < OZ_SMAX; ++gI)
+                        if (gI < s)
+                            tmem_ld8(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(gI * OZ_BN + 8 * b), r[gI]);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = fma(v[j], 0.00390625, (double)(int)r[j]);
-                }
+                    for (int j = 0; j < 8; ++j) v[b][j] = 0.0;
 #pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    const int col = n0 + c0 + j;
-                    const double f0 = scalbn(sa, max(ebz[col], -1022)), f1 = scalbn(sa, max(ebz[col + 1], -1022));
-                    double2 out = make_double2(p.alpha * f0 * v[j], p.alpha * f1 * v[j + 1]);
-                    double2* dst = reinterpret_cast<double2*>(crow + c0 + j);
-                    if (beta != 0.0) {
-                        const double2 old = *dst;
-                        out.x = fma(beta, old.x, out.x);
-                        out.y = fma(beta, old.y, out.y);
-                    }
-                    *dst = out;
+                    for (int gI = OZ_SMAX - 1; gI >= 0; --gI)
+                        if (gI < s) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[b][j] = fma(v[b][j], 0.00390625, i32_to_f64(r[gI][j]));
+                        }
                 }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_(smem_u32(&acc_empty));
+                if (warp == 2 && lane == 0) OZ_STAMP(3);
+
+                // phase B: 16 columns at a time through the staging tile
+#pragma unroll
+                for (int q4 = 0; q4 < OZ_BN / 16; ++q4) {
+                    const int c0 = 16 * q4;
+                    double oldv[16];
+                    if (beta != 0.0) {   // 16 independent coalesced loads in flight
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) oldv[i] = cw[(long long)(2 * i + rsub) * p.ldc + c0 + col];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)   // 16-byte chunk c of row `lane` lands at chunk c ^ (lane & 7)
+                        *reinterpret_cast<double2*>(stg + lane * 16 + ((c ^ (lane & 7)) << 1)) =
+                            make_double2(sa * v[2 * q4 + (c >> 2)][2 * (c & 3)], sa * v[2 * q4 + (c >> 2)][2 * (c & 3) + 1]);
+                    __syncwarp();
+                    const double fcol = scalbn(1.0, max(ebz[c0 + col], -1022));
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int rr = 2 * i + rsub;
+                        double out = stg[rr * 16 + ((((col >> 1) ^ (rr & 7)) << 1) | (col & 1))] * fcol;
+                        if (beta != 0.0) out = fma(beta, oldv[i], out);
+                        cw[(long long)rr * p.ldc + c0 + col] = out;
+                    }
+                    __syncwarp();
+                }
+                if (warp == 2 && lane == 0) OZ_STAMP(4);
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive_(smem_u32(&acc_empty));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -412,6 +497,8 @@ __global__ void __launch_bounds__(256) slice_mc_kernel(const double* __restrict_
 // host side
 // ------------------------------------------------------------------------------------------
 static bool g_oz_attr = false;
+static long long* g_oz_dbg = nullptr;
+static int g_oz_sms = 148;   // CTAs of the persistent kernel (one per SM)
 
 // scratch for ONE batch member (tile images of both operands + exponents)
 long long ozaki_ws_bytes(int M, int N, int K, int s, bool same_operand) {
@@ -426,7 +513,7 @@ int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA,
                long long sB, double* C, long long ldc, long long sC, int M, int N, int K, double alpha, double beta,
                int lower, int s, bool same_operand, int batch, void* ws, long long ws_bytes, cudaStream_t st) {
     if (s < 1 || s > OZ_SMAX || (M % OZ_BM) || (N % OZ_BM) || (K % 32) || batch < 1) return PLMC_ERR_BADARG;
-    if (same_operand && (M != N)) return PLMC_ERR_BADARG;
+    if ((same_operand || lower) && (M != N)) return PLMC_ERR_BADARG;
     const long long pad = 1024;
     uint8_t* w0 = (uint8_t*)(((uintptr_t)ws + pad - 1) / pad * pad);
     const long long avail = ws_bytes - (long long)(w0 - (uint8_t*)ws);
@@ -436,12 +523,18 @@ int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA,
     const long long bytesA = (long long)s * M * K;                       // multiple of 4096
     const long long bytesB = same_operand ? 0 : (long long)s * N * K;
     if (!g_oz_attr) {
-        if (cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 OZ_STAGES * oz_stage_bytes(OZ_SMAX) + 1024) != cudaSuccess)
+        int smem_max = 0;
+        for (int t = 1; t <= OZ_SMAX; ++t) smem_max = oz_smem_bytes(t) > smem_max ? oz_smem_bytes(t) : smem_max;
+        if (cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) !=
+            cudaSuccess)
             return PLMC_ERR_LAUNCH;
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            g_oz_sms = sms;
         g_oz_attr = true;
     }
-    const int smem = OZ_STAGES * oz_stage_bytes(s) + 1024;
+    const int smem = oz_smem_bytes(s);
 
     for (int b0 = 0; b0 < batch; b0 += bc_max) {
         const int bc = (batch - b0) < bc_max ? (batch - b0) : bc_max;
@@ -469,7 +562,13 @@ int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA,
         p.ea = ea; p.eb = eb;
         p.M = M; p.N = N; p.K = K; p.s = s;
         p.alpha = alpha; p.beta = beta; p.lower = lower;
-        ozaki_gemm_kernel<<<dim3((unsigned)((N / OZ_BN) * (M / OZ_BM)), 1, bc), OZ_THREADS, smem, st>>>(p);
+        const long long tiles_m = M / OZ_BM;
+        const long long per = lower ? tiles_m * (tiles_m + 1) : tiles_m * (N / OZ_BN);
+        if (per * bc > 2000000000LL) return PLMC_ERR_BADARG;
+        p.per_member = (int)per; p.total = (int)(per * bc);
+        p.dbg = g_oz_dbg;
+        const int ctas = p.total < g_oz_sms ? p.total : g_oz_sms;
+        ozaki_gemm_kernel<<<ctas, OZ_THREADS, smem, st>>>(p);
         PLMC_CHECK_LAUNCH();
         note_launch(3);
     }
@@ -479,6 +578,11 @@ int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA,
 }  // namespace plmc
 
 extern "C" {
+
+int plmc_ozaki_debug(long long* stamps) {
+    plmc::g_oz_dbg = stamps;
+    return PLMC_OK;
+}
 
 long long plmc_ozaki_ws_bytes(int M, int N, int K, int slices, int same_operand) {
     return plmc::ozaki_ws_bytes(M, N, K, slices, same_operand != 0);

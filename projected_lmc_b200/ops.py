@@ -228,6 +228,15 @@ def stats_reset():
     check(_cabi.load().plmc_stats_reset(), "stats_reset")
 
 
+def trace_enable(on: bool):
+    """Per-shape CUDA-event timing of every GEMM of the factorisation layer (diagnostics)."""
+    check(_cabi.load().plmc_trace_enable(int(bool(on))), "trace_enable")
+
+
+def trace_report():
+    check(_cabi.load().plmc_trace_report(), "trace_report")
+
+
 def stats_get():
     """(kernel launches, GEMM launches, GEMM algorithmic FLOPs) since the last reset."""
     import ctypes
