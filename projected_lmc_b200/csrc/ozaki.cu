@@ -37,8 +37,9 @@ namespace plmc {
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_BK = 32;   // BK in int8 elements = bytes
 constexpr int OZ_SMAX = 7;                           // TMEM: 7 accumulators x 64 columns = 448 <= 512
 constexpr int OZ_STAGES = 5;                         // ring depth (4 at s = 7: 227 KB of shared memory per CTA)
-constexpr int OZ_STG_BYTES = 4 * 4096;               // epilogue staging: one 32 x 16 FP64 block per epilogue warp
-constexpr int OZ_THREADS = 192;                      // warp0 producer, warp1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int OZ_EPI_WARPS = 8;                      // two per TMEM lane quarter, 32 columns each
+constexpr int OZ_STG_BYTES = OZ_EPI_WARPS * 4096;    // epilogue staging: one 32 x 16 FP64 block per epilogue warp
+constexpr int OZ_THREADS = 64 + 32 * OZ_EPI_WARPS;   // warp0 producer, warp1 MMA + TMEM alloc, warps 2.. epilogue
 constexpr int OZ_KCHUNK = 16384;                     // INT32 exactness: 7 * 16384 * 128^2 < 2^31
 constexpr int OZ_IMG = OZ_BM * OZ_BK;                // 4096 B: one plane of one (128-row, 32-k) tile
 constexpr int OZ_B_PLANE = OZ_BN * OZ_BK;            // 2048 B: half an image
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzArgs 
             mbar_init_(smem_u32(&empty_bar[i]), 1);
         }
         mbar_init_(smem_u32(&acc_full), 1);
-        mbar_init_(smem_u32(&acc_empty), 4);
+        mbar_init_(smem_u32(&acc_empty), OZ_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -301,7 +302,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzArgs 
         // block of the warp is then turned through a swizzled staging tile so that global loads (beta) and
         // stores run along rows: 16 lanes x 8 B = one full 128-byte line per half warp.
         const int quad = warp & 3;                 // TMEM lane quarter this warp may access
-        double* stg = reinterpret_cast<double*>(stg_base + quad * 4096);
+        const int half = (warp - 2) >> 2;          // which 32 of the 64 columns
+        double* stg = reinterpret_cast<double*>(stg_base + (warp - 2) * 4096);
         const int rsub = lane >> 4, col = lane & 15;
         int phase = 0;
         int nt = 0;
@@ -317,17 +319,18 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzArgs 
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (warp == 2 && lane == 0) OZ_STAMP(2);
                 const double beta = (ch > 0) ? 1.0 : p.beta;   // later K-chunks accumulate onto the first
-                // phase A: drain TMEM.  v[b][j] = sum_g 2^-8g D_g[row][8 b + j], all 64 columns of the row kept
+                // phase A: drain TMEM.  v[b][j] = sum_g 2^-8g D_g[row][8 b + j], this warp's 32 columns of the row kept
                 // in registers, so the accumulators go back to the MMA warp after ~3 us and the read-modify-
                 // write of C below overlaps the next tile's main loop.
-                double v[OZ_BN / 8][8];
+                double v[OZ_BN / 16][8];
 #pragma unroll
-                for (int b = 0; b < OZ_BN / 8; ++b) {
+                for (int b = 0; b < OZ_BN / 16; ++b) {
                     uint32_t r[OZ_SMAX][8];
 #pragma unroll
                     for (int gI = 0; gI < OZ_SMAX; ++gI)
                         if (gI < s)
-                            tmem_ld8(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(gI * OZ_BN + 8 * b), r[gI]);
+                            tmem_ld8(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(gI * OZ_BN + 32 * half + 8 * b),
+                                     r[gI]);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[b][j] = 0.0;
@@ -345,8 +348,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) ozaki_gemm_kernel(const OzArgs 
 
                 // phase B: 16 columns at a time through the staging tile
 #pragma unroll
-                for (int q4 = 0; q4 < OZ_BN / 16; ++q4) {
-                    const int c0 = 16 * q4;
+                for (int q4 = 0; q4 < OZ_BN / 32; ++q4) {
+                    const int c0 = 32 * half + 16 * q4;
                     double oldv[16];
                     if (beta != 0.0) {   // 16 independent coalesced loads in flight
 #pragma unroll

@@ -9,6 +9,7 @@
 //   * nothing here allocates, frees or synchronises the device: all work is
 //     stream-ordered on the stream handed in through the C ABI.
 #pragma once
+#include <cstdio>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -21,7 +22,10 @@
 #define PLMC_CHECK_LAUNCH()                              \
     do {                                                 \
         cudaError_t e__ = cudaGetLastError();            \
-        if (e__ != cudaSuccess) return PLMC_ERR_LAUNCH;  \
+        if (e__ != cudaSuccess) {                        \
+            fprintf(stderr, "libplmc_b200: %s at %s:%d\n", cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return PLMC_ERR_LAUNCH;                      \
+        }                                                \
     } while (0)
 
 namespace plmc {
