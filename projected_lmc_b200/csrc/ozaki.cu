@@ -394,27 +394,36 @@ __device__ __forceinline__ int exp_for(double amax) {
 }
 
 // 4 consecutive k (k4 % 4 == 0) of row x with row exponent e (|v| * 2^-e < 1): one 32-bit store per plane.
-// Balanced base-256 digits of Q = rint(v * 2^(8s-2-e)), least significant first.
+// Q = rint(v * 2^(8s-2-e)); adding 0x80 to every byte position turns the balanced base-256 digits of Q
+// into the plain bytes of Q + 0x80..80, and x - 128 (mod 256) is x ^ 0x80: so the digits of one element
+// cost one 64-bit add and xor, and PRMT gathers byte (s-1-i) of the four elements into the word of plane i.
 __device__ __forceinline__ void slice4_store(const double (&v)[4], int e, int x, int k4, int s, int nkt,
                                              int8_t* planes) {
     int8_t* dst = planes + img_offset(x, k4, 0, s, nkt);
-    long long Q[4];
+    const int sh = 8 * s - 2 - e;                                   // |sh| < 1100: split, 2^sh may overflow
+    const double m1 = __longlong_as_double((long long)(1023 + sh / 2) << 52);        // 2^(sh/2), exponent field
+    const double m2 = __longlong_as_double((long long)(1023 + sh - sh / 2) << 52);
+    const unsigned long long bias = 0x8080808080808080ull >> (8 * (8 - s));
+    uint32_t lo[4], hi[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) Q[u] = __double2ll_rn(scalbn(v[u], 8 * s - 2 - e));
-    for (int i = s - 1; i >= 0; --i) {
-        uint32_t pack = 0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int d = (i > 0) ? (int)((Q[u] + 128) & 255) - 128 : (int)Q[u];
-            Q[u] = (Q[u] - d) >> 8;
-            pack |= ((uint32_t)(uint8_t)(int8_t)d) << (8 * u);
-        }
-        *reinterpret_cast<uint32_t*>(dst + (long long)i * OZ_IMG) = pack;
+    for (int u = 0; u < 4; ++u) {
+        const unsigned long long q =
+            ((unsigned long long)__double2ll_rn(v[u] * m1 * m2) + bias) ^ 0x8080808080808080ull;
+        lo[u] = (uint32_t)q;
+        hi[u] = (uint32_t)(q >> 32);
+    }
+    for (int i = 0; i < s; ++i) {
+        const int b = s - 1 - i;                                    // byte of Q that is the digit of plane i
+        const bool h = b >= 4;
+        const uint32_t sel = (uint32_t)(b & 3) | ((uint32_t)(4 + (b & 3)) << 4);
+        const uint32_t t01 = __byte_perm(h ? hi[0] : lo[0], h ? hi[1] : lo[1], sel);
+        const uint32_t t23 = __byte_perm(h ? hi[2] : lo[2], h ? hi[3] : lo[3], sel);
+        *reinterpret_cast<uint32_t*>(dst + (long long)i * OZ_IMG) = __byte_perm(t01, t23, 0x5410);
     }
 }
 
 // one CTA per row (KC): coalesced along k
-__global__ void __launch_bounds__(256) slice_kc_kernel(const double* __restrict__ Pb, long long ld, long long sP,
+__global__ void __launch_bounds__(256) slice_kc_row_kernel(const double* __restrict__ Pb, long long ld, long long sP,
                                                        int X, int K, int s, int8_t* __restrict__ planes_b,
                                                        long long sPl, int* __restrict__ ex_b) {
     __shared__ double red[8];
@@ -447,6 +456,70 @@ __global__ void __launch_bounds__(256) slice_kc_kernel(const double* __restrict_
     }
 }
 
+// KC operand: one WARP per row (8 rows per CTA, no block-level synchronisation).  Rows of up to
+// 128 * NCH elements stay in registers between the absmax pass and the slicing pass; longer rows are
+// read twice (the second time from L1/L2).
+template <int NCH>
+__global__ void __launch_bounds__(256) slice_kc_kernel(const double* __restrict__ Pb, long long ld, long long sP,
+                                                       int X, int K, int s, int8_t* __restrict__ planes_b,
+                                                       long long sPl, int* __restrict__ ex_b) {
+    const int lane = threadIdx.x & 31;
+    const int x = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (x >= X) return;
+    const double* row = Pb + (long long)blockIdx.z * sP + (long long)x * ld;
+    int8_t* planes = planes_b + (long long)blockIdx.z * sPl;
+    const int nkt = K / OZ_BK;
+    const bool al16 = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+    auto load4 = [&](int k4, double (&v)[4]) {
+        if (al16) {
+            const double2 a = *reinterpret_cast<const double2*>(row + k4);
+            const double2 b = *reinterpret_cast<const double2*>(row + k4 + 2);
+            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = row[k4 + u];
+        }
+    };
+    double amax = 0.0;
+    if (NCH > 0) {
+        double v[NCH > 0 ? NCH : 1][4];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int k4 = c * 128 + lane * 4;
+            if (k4 < K) {
+                load4(k4, v[c]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) amax = fmax(amax, fabs(v[c][u]));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        const int e = exp_for(amax);
+        if (lane == 0) ex_b[(long long)blockIdx.z * X + x] = e;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int k4 = c * 128 + lane * 4;
+            if (k4 < K) slice4_store(v[c], e, x, k4, s, nkt, planes);
+        }
+    } else {
+        for (int k4 = lane * 4; k4 < K; k4 += 128) {
+            double v[4];
+            load4(k4, v);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) amax = fmax(amax, fabs(v[u]));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        const int e = exp_for(amax);
+        if (lane == 0) ex_b[(long long)blockIdx.z * X + x] = e;
+        for (int k4 = lane * 4; k4 < K; k4 += 128) {
+            double v[4];
+            load4(k4, v);
+            slice4_store(v, e, x, k4, s, nkt, planes);
+        }
+    }
+}
+
 // MC operand, pass 1: exponent of the column-wise absmax over k.  The frexp exponent is monotone in
 // |x|, so the maximum of the per-element exponents is taken with an integer atomicMax over k-slabs
 // (order independent -> deterministic).  ex must be pre-set to a very negative value (memset 0x80).
@@ -475,25 +548,35 @@ __global__ void __launch_bounds__(256) absmax_mc_kernel(const double* __restrict
     }
 }
 
-// MC operand, pass 2: 32(k) x 32(x) tiles transposed through shared memory
+// MC operand, pass 2: 32(k) x 128(x) tiles transposed through shared memory; one CTA writes one whole
+// 4096-byte image per plane (8 lanes cover the 32 bytes of a row, 4 rows per warp store)
 __global__ void __launch_bounds__(256) slice_mc_kernel(const double* __restrict__ Pb, long long ld, long long sP,
                                                        int X, int K, int s, int8_t* __restrict__ planes_b,
                                                        long long sPl, const int* __restrict__ ex_b) {
-    __shared__ double tile[32][33];
+    __shared__ double tile[32][129];
     const double* P = Pb + (long long)blockIdx.z * sP;
     int8_t* planes = planes_b + (long long)blockIdx.z * sPl;
     const int* ex = ex_b + (long long)blockIdx.z * X;
-    const int x0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows of 32
-    for (int r = ty; r < 32; r += 8) tile[r][tx] = P[(long long)(k0 + r) * ld + x0 + tx];   // tile[k][x]
-    __syncthreads();
-    // thread -> (x = threadIdx.x / 8, 4 consecutive k = (threadIdx.x % 8) * 4)
-    const int xl = threadIdx.x >> 3, kl = (threadIdx.x & 7) * 4;
-    const int e = max(ex[x0 + xl], -1022);   // all-zero column: any exponent works
-    double v[4];
+    const int x0 = blockIdx.x * 128, k0 = blockIdx.y * 32;
+    {
+        const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;   // 2 k-rows of 128 x per pass
+        double t[16];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = tile[kl + u][xl];
-    slice4_store(v, e, x0 + xl, k0 + kl, s, K / OZ_BK, planes);
+        for (int i = 0; i < 16; ++i) t[i] = P[(long long)(k0 + 2 * i + ty) * ld + x0 + tx];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) tile[2 * i + ty][tx] = t[i];
+    }
+    __syncthreads();
+    const int kl = (threadIdx.x & 7) * 4;
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+        const int xl = pass * 32 + (threadIdx.x >> 3);
+        const int e = max(ex[x0 + xl], -1022);   // all-zero column: any exponent works
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = tile[kl + u][xl];
+        slice4_store(v, e, x0 + xl, k0 + kl, s, K / OZ_BK, planes);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -549,11 +632,14 @@ int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA,
         auto slice = [&](bool kc, const double* P, long long ld, long long sP, int X, int8_t* planes,
                          long long sPl, int* ex) {
             if (kc) {
-                slice_kc_kernel<<<dim3(X, 1, bc), 256, 0, st>>>(P, ld, sP, X, K, s, planes, sPl, ex);
+                const dim3 g((X + 7) / 8, 1, bc);
+                if (K <= 512) slice_kc_kernel<4><<<g, 256, 0, st>>>(P, ld, sP, X, K, s, planes, sPl, ex);
+                else if (K <= 1024) slice_kc_kernel<8><<<g, 256, 0, st>>>(P, ld, sP, X, K, s, planes, sPl, ex);
+                else slice_kc_row_kernel<<<dim3(X, 1, bc), 256, 0, st>>>(P, ld, sP, X, K, s, planes, sPl, ex);
             } else {
                 cudaMemsetAsync(ex, 0x80, sizeof(int) * (size_t)X * bc, st);
                 absmax_mc_kernel<<<dim3((X + 63) / 64, (K + 255) / 256, bc), 256, 0, st>>>(P, ld, sP, X, K, ex);
-                slice_mc_kernel<<<dim3(X / 32, K / 32, bc), 256, 0, st>>>(P, ld, sP, X, K, s, planes, sPl, ex);
+                slice_mc_kernel<<<dim3(X / 128, K / 32, bc), 256, 0, st>>>(P, ld, sP, X, K, s, planes, sPl, ex);
             }
         };
         slice(aKC, A + (long long)b0 * sA, lda, sA, M, pa, bytesA, ea);
