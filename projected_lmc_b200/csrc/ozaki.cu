@@ -603,7 +603,9 @@ int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA,
     const long long pad = 1024;
     uint8_t* w0 = (uint8_t*)(((uintptr_t)ws + pad - 1) / pad * pad);
     const long long avail = ws_bytes - (long long)(w0 - (uint8_t*)ws);
-    const long long need1 = ozaki_ws_bytes(M, N, K, s, same_operand);
+    // ozaki_ws_bytes carries one extra `pad` so that a scratch of exactly that size still fits after
+    // the base pointer has been rounded up to 1024 bytes
+    const long long need1 = ozaki_ws_bytes(M, N, K, s, same_operand) - pad;
     if (avail < need1) return PLMC_ERR_BADARG;
     const int bc_max = (int)((avail / need1) < batch ? (avail / need1) : batch);
     const long long bytesA = (long long)s * M * K;                       // multiple of 4096

@@ -247,7 +247,7 @@ def stats_get():
 
 
 def ozaki_gemm(layout, A, B, C, M, N, K, alpha=1.0, beta=0.0, lower=False, slices=7, same_operand=False, ws=None):
-    """C = alpha op(A) op(B) + beta C (2-D views) on the tcgen05 INT8 path; beta in {0, 1}."""
+    """C = alpha op(A) op(B) + beta C (2-D views) on the tcgen05 INT8 path (FP64 via 8-bit planes)."""
     need = lib().plmc_ozaki_ws_bytes(M, N, K, slices, int(same_operand))
     if ws is None or ws.numel() < need:
         ws = torch.empty((need,), dtype=torch.uint8, device=C.device)

@@ -47,6 +47,38 @@ def test_single_plane_inputs_are_exact():
     assert torch.equal(C, A @ B.T)
 
 
+def test_scratch_of_exactly_the_advertised_size_at_any_alignment():
+    M, N, K = 256, 128, 256
+    A, B = rnd(M, K, seed=12), rnd(N, K, seed=13)
+    need = ops.lib().plmc_ozaki_ws_bytes(M, N, K, 7, 0)
+    buf = torch.empty(need + 2048, dtype=torch.uint8, device=DEV)
+    for off in (0, 8, 520, 1016):
+        C = torch.empty(M, N, dtype=torch.float64, device=DEV)
+        ops.ozaki_gemm(0, A, B, C, M, N, K, slices=7, ws=buf[off:off + need])
+        assert rel_err(C, A @ B.T) < 1e-13
+
+
+def test_lower_needs_a_square_product():
+    A, B = rnd(256, 64, seed=14), rnd(128, 64, seed=15)
+    C = torch.zeros(256, 128, dtype=torch.float64, device=DEV)
+    with pytest.raises(Exception):
+        ops.ozaki_gemm(0, A, B, C, 256, 128, 64, lower=True)
+
+
+def test_gemm_trace_reports_every_shape(capfd):
+    X, Y, _, _ = synth(1500, 3, 4, 2, seed=5)
+    m = make_model(X, Y, 2, variant="PLMC", kernel="rbf").cuda()
+    ops.trace_enable(True)
+    try:
+        loss = -ProjectedLMCmll(m.likelihood, m)(m(X.cuda()), Y.cuda())
+        loss.backward()
+    finally:
+        ops.trace_report()
+        ops.trace_enable(False)
+    err = capfd.readouterr().err
+    assert "TFLOP/s" in err and ("int8" in err or "dmma" in err)
+
+
 def test_rows_with_very_different_scales_and_zero_rows():
     M, N, K = 256, 256, 256
     A, B = rnd(M, K, seed=4), rnd(N, K, seed=5)
