@@ -181,6 +181,14 @@ def roofline_entry(eng, achieved, dmma_peak, peaks, peak_src, gemm_flops, gemm_l
         bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
         peak = 2.0 * bf16 / pairs
         common.update({
+            # one ncu --set full capture of ozaki_gemm_kernel (8192^3, 7 slices): dram read 7.91 GB + write 0.60 GB
+            # per launch against 1.47 GB algorithmic (planes once + C once); re-reads are L2 misses of the
+            # streamed B planes, the kernel runs at 0.68 TB/s: not traffic bound
+            "traffic": 8.50e9,
+            "traffic_reference": "ncu --set full, one 8192^3 ozaki_gemm_kernel launch (profiles/"
+                                 "r01_ozaki_gemm_v2_ncu_summary.md): 7.91 GB read + 0.60 GB written per launch, "
+                                 "1.47 GB algorithmic, 0.68 TB/s: not traffic bound; tensor pipe (UTCIMMA) 54 % of "
+                                 "nominal, power-capped",
             "kernel": "ozaki_gemm_kernel (FP64 GEMM as %d INT8 tcgen05.mma products, TMA + TMEM) for GEMMs >= %d; "
                       "gemm_dmma_kernel (DMMA.8x8x4) below" % (pairs, eng.fp64_min_dim),
             "peak": peak, "frac": (achieved / peak) if achieved else None,
