@@ -5,7 +5,7 @@ The public model API (``ProjectedGPModel``, ``ProjectedLMCmll`` ...) mirrors
 hand-written CUDA kernels behind the C ABI in ``include/plmc_b200.h``.
 """
 from . import gp  # noqa: F401
-from .engine import LatentEngine, NotPSDError  # noqa: F401
+from .engine import LatentEngine, NanError, NotPSDError  # noqa: F401
 from .mixing import (LMCMixingMatrix, LowerTriangularParam, PositiveDiagonalParam, ScalarParam,  # noqa: F401
                      UpperTriangularParam)
 from .mll import ProjectedLMCmll, projection_terms  # noqa: F401
@@ -16,5 +16,5 @@ __version__ = "0.1.0"
 __all__ = [
     "gp", "ProjectedGPModel", "ProjectedLMCmll", "ExactGPModel", "LMCMixingMatrix", "ScalarParam",
     "PositiveDiagonalParam", "UpperTriangularParam", "LowerTriangularParam", "handle_covar_",
-    "init_lmc_coefficients", "LatentEngine", "NotPSDError", "projection_terms", "fit",
+    "init_lmc_coefficients", "LatentEngine", "NotPSDError", "NanError", "projection_terms", "fit",
 ]

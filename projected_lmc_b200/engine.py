@@ -29,6 +29,10 @@ class NotPSDError(RuntimeError):
     pass
 
 
+class NanError(RuntimeError):
+    """Raised where linear_operator's psd_safe_cholesky raises its NanError (NaN in the matrix to factor)."""
+
+
 class LatentEngine:
     def __init__(self):
         self._ws = None
@@ -93,6 +97,15 @@ class LatentEngine:
         q = Z.shape[0]
         K, dinv, info = ws["K"], ws["dinv"], ws["info"]
         jitter = torch.zeros(q, dtype=torch.float64, device=Z.device)
+        # psd_safe_cholesky refuses a matrix with NaN entries before it factors anything.  Every entry of K is a
+        # function of zn, Z, the outputscale and the noise, so the O(qn) inputs are checked instead of the n^2
+        # matrix (the integer tensor path would turn a NaN into an arbitrary finite number, not propagate it).
+        finite = torch.isfinite(zn).all() & torch.isfinite(noise).all()
+        if os_ is not None:
+            finite = finite & torch.isfinite(os_).all()
+        if not bool(finite):
+            raise NanError("cholesky: the kernel matrix contains NaN (non-finite inputs, lengthscales, outputscale "
+                           "or noise)")
         ops.gram(Z, zn, kid, os_, noise, K, n)
         self._mark("gram")
         ops.potrf(K, dinv, info)

@@ -253,3 +253,14 @@ def test_not_psd_error_after_max_tries():
         # a jitter far below the rounding level cannot repair the singular matrix
         with gp.settings.cholesky_max_tries(2), gp.settings.cholesky_jitter(1e-40), pytest.raises(NotPSDError):
             ProjectedLMCmll(m.likelihood, m)(m(X.cuda()), Y.cuda())
+
+
+def test_nan_inputs_raise_like_psd_safe_cholesky():
+    """linear_operator's psd_safe_cholesky raises NanError on a matrix with NaN entries before factoring."""
+    from projected_lmc_b200 import NanError
+
+    X, Y, _, _ = synth(300, 3, 4, 2)
+    X[17, 1] = float("nan")
+    m = make_model(X, Y, 2, variant="PLMC", kernel="rbf").cuda()
+    with pytest.raises(NanError):
+        ProjectedLMCmll(m.likelihood, m)(m(m.train_inputs[0]), Y.cuda())
