@@ -376,6 +376,13 @@ class ProjectedGPModel(ExactGPModel):
         with torch.no_grad():
             st = self._prediction_state()
             xs = _as_f64(x if x.dim() > 1 else x.unsqueeze(-1)).contiguous()
+            # a non-finite test point gives NaN predictions for that point in the reference; the integer tensor
+            # path of the solve would not propagate it, so such rows are computed at 0 and overwritten below
+            bad_rows = ~torch.isfinite(xs).all(dim=1)
+            has_bad = bool(bad_rows.any())
+            if has_bad:
+                xs = xs.clone()
+                xs[bad_rows] = 0.0
             lat_mean, lat_var = self._engine.predict_latents(st, xs)
             lo, hi = self._latent_range
             Ht = _as_f64(self.lmc_coefficients())[lo:hi].contiguous()
@@ -389,6 +396,9 @@ class ProjectedGPModel(ExactGPModel):
                 import torch.distributed as dist
                 dist.all_reduce(mean, group=self._dist_group)
                 dist.all_reduce(var, group=self._dist_group)
+            if has_bad:
+                mean[bad_rows] = float("nan")
+                var[bad_rows] = float("nan")
         return gp.distributions.MultitaskMultivariateNormal(mean.to(x.dtype), var.to(x.dtype))
 
 

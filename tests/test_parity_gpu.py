@@ -264,3 +264,19 @@ def test_nan_inputs_raise_like_psd_safe_cholesky():
     m = make_model(X, Y, 2, variant="PLMC", kernel="rbf").cuda()
     with pytest.raises(NanError):
         ProjectedLMCmll(m.likelihood, m)(m(m.train_inputs[0]), Y.cuda())
+
+
+def test_non_finite_test_points_give_nan_rows_only():
+    X, Y, Xs, _ = synth(400, 3, 4, 2, ns=20)
+    m = make_model(X, Y, 2, variant="PLMC", kernel="matern52").cuda()
+    m.eval()
+    with torch.no_grad():
+        good = m(Xs.cuda())
+        Xb = Xs.clone()
+        Xb[3, 0] = float("nan")
+        Xb[11, 2] = float("inf")
+        pred = m(Xb.cuda())
+    keep = torch.ones(20, dtype=torch.bool)
+    keep[[3, 11]] = False
+    assert torch.isnan(pred.mean[~keep]).all() and torch.isnan(pred.variance[~keep]).all()
+    assert torch.equal(pred.mean[keep], good.mean[keep]) and torch.equal(pred.variance[keep], good.variance[keep])
