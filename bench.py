@@ -178,8 +178,12 @@ def roofline_entry(eng, achieved, dmma_peak, peaks, peak_src, gemm_flops, gemm_l
     }
     if s > 0:
         pairs = s * (s + 1) // 2
+        # potrf and trtri (2/3 of the q*n^3 FLOP) use s slices, lauum (1/3) fp64_slices_kinv: the roof is taken
+        # with the flop-weighted number of INT8 products per FP64 product
+        sk = min(getattr(eng, "fp64_slices_kinv", 0) or s, s)
+        pairs_eff = (2.0 * pairs + sk * (sk + 1) // 2) / 3.0
         bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
-        peak = 2.0 * bf16 / pairs
+        peak = 2.0 * bf16 / pairs_eff
         common.update({
             # one ncu --set full capture of ozaki_gemm_kernel (8192^3, 7 slices): dram read 7.91 GB + write 0.60 GB
             # per launch against 1.47 GB algorithmic (planes once + C once); re-reads are L2 misses of the
@@ -192,8 +196,8 @@ def roofline_entry(eng, achieved, dmma_peak, peaks, peak_src, gemm_flops, gemm_l
             "kernel": "ozaki_gemm_kernel (FP64 GEMM as %d INT8 tcgen05.mma products, TMA + TMEM) for GEMMs >= %d; "
                       "gemm_dmma_kernel (DMMA.8x8x4) below" % (pairs, eng.fp64_min_dim),
             "peak": peak, "frac": (achieved / peak) if achieved else None,
-            "peak_source": "2 x %s bf16 sustained (%.0f TFLOP/s) / %d INT8 products per FP64 product (%d slices)"
-                           % (peak_src, bf16, pairs, s),
+            "peak_source": "2 x %s bf16 sustained (%.0f TFLOP/s) / %.2f INT8 products per FP64 product "
+                           "(%d slices in potrf/trtri, %d in lauum, flop-weighted)" % (peak_src, bf16, pairs_eff, s, sk),
             "how": "algorithmic q*n^3 FLOP per step / CUDA-event time of the potrf+solve+potri phases",
         })
     else:

@@ -5,7 +5,7 @@
 // Why: B200 has no FP64 kind on tcgen05 and its DMMA/DFMA datapath tops out at
 // 37 TFLOP/s (measured; the two share one unit, see plmc_peak_mixed).  The INT8
 // tensor path is two orders of magnitude wider, so a product of two FP64 matrices
-// split into s planes of 7 bits costs s(s+1)/2 INT8 GEMMs and still wins.
+// split into s 8-bit planes costs s(s+1)/2 INT8 GEMMs and still wins.
 //
 //   x = A[m,k] * 2^-(ea[m]+1)  (|x| < 1/2),  Q = rint(x * 2^(8s-1))  (a 64-bit integer, exact up to the rounding)
 //   Q = sum_i a_i 256^(s-1-i) with BALANCED base-256 digits a_i in [-128, 127] (a_0 in [-65, 65]):
@@ -26,8 +26,8 @@
 // L1TEX->XBAR request rate, ncu: l1tex__m_l1tex2xbar_req_cycles_active 83 %.)
 //
 // Kernel: persistent, one CTA per SM walking 128 x 64 output tiles; warp 0 = copy producer (runs ahead
-// into the next tile), warp 1 = MMA issuer (one elected thread), warps 2..5 = epilogue.  s accumulators (one per diagonal g, 64
-// TMEM columns each, 448 of 512 columns at s = 7).  All pairs (i, j) of one A plane i are a
+// into the next tile), warp 1 = MMA issuer (one elected thread), warps 2..9 = epilogue (two per TMEM lane
+// quarter).  s accumulators (one per diagonal g, 64 TMEM columns each, 448 of 512 columns at s = 7).  All pairs (i, j) of one A plane i are a
 // single wide MMA: their accumulators g = i..s-1 are consecutive TMEM column blocks and the
 // B planes consecutive shared-memory row blocks, so A_i is read from shared memory once.
 #include "plmc_common.cuh"
@@ -112,15 +112,6 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                  : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])

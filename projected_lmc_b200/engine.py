@@ -65,6 +65,11 @@ class LatentEngine:
     # whole test-suite can be run in either mode.
     fp64_slices = int(__import__("os").environ.get("PLMC_FP64_SLICES", "7"))
     fp64_min_dim = int(__import__("os").environ.get("PLMC_FP64_MIN_DIM", "512"))
+    # slices for the LAUUM step of the training iteration (K^-1 = L^-T L^-1).  K^-1 feeds ONLY the gradient sweep
+    # tr((alpha alpha^T - K^-1) dK): the loss, alpha and the log-determinant come from L and L^-1, which keep
+    # fp64_slices.  47-bit products there perturb the gradients at the 1e-12 level (tolerance 1e-6) and save a
+    # quarter of the LAUUM time; 0 = same as fp64_slices.
+    fp64_slices_kinv = int(__import__("os").environ.get("PLMC_FP64_SLICES_KINV", "6"))
     _oz = None
 
     def _configure_fp64(self, device, np_, q=1):
@@ -159,7 +164,15 @@ class LatentEngine:
         z, alpha, quad, logdet = ops.trmv_solve_logdet(K, TY, n, ws["rhs"])
         lp = -0.5 * (quad + logdet + n * math.log(2 * math.pi))
         mark("solve_logdet")
-        ops.lauum(K)
+        s_kinv = min(self.fp64_slices_kinv, self.fp64_slices)
+        lower = self._oz is not None and 0 < s_kinv < self.fp64_slices and np_ >= 2 * self.fp64_min_dim
+        if lower:
+            ops.set_fp64_emulation(self._oz, s_kinv, self.fp64_min_dim)
+        try:
+            ops.lauum(K)
+        finally:
+            if lower:
+                ops.set_fp64_emulation(self._oz, self.fp64_slices, self.fp64_min_dim)
         mark("potri")
         g_ell, g_os, g_noise = ops.grad_sweep(K, alpha, Z, zn, ell, kid, os_, n)
         mark("grad_sweep")
