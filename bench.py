@@ -8,7 +8,8 @@ Workload (BASELINE.json configs[1]): synthetic SARCOS-shaped projected LMC,
 n = 44,484 points, d = 21, Matern-5/2 ARD, fp64, PLMC variant; 4 latents and 7 tasks
 PER GPU (weak scaling: at N GPUs the model has 4N latents / 7N tasks, each rank owns 4
 latents, one NCCL all-reduce of the loss + gradients per step).  One step = one training
-iteration = MLL forward + full backward to every raw parameter.  `value` counts
+iteration of the reference's loop (experiments.py:263-273): zero_grad, MLL forward, full backward to
+every raw parameter, AdamW step, learning-rate scheduler step.  `value` counts
 4-latent SARCOS-shaped model iterations per second (N per step at N GPUs).
 """
 from __future__ import annotations
@@ -222,12 +223,13 @@ def oracle_iteration_time(cfg, n_s, steps, warmup, world=1):
     X, Y = make_data(n_s, cfg["d"], cfg["p"] * world, cfg["q"] * world, seed=1)
     m = build_model(X, Y, cfg["q"] * world, cfg["kernel"])
     times = []
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-2)
     for it in range(warmup + steps):
-        for prm in m.parameters():
-            prm.grad = None
         t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
         loss = -O.mll(oracle_params(m), X, Y)
         loss.backward()
+        opt.step()
         t1 = time.perf_counter()
         if it >= warmup:
             times.append(t1 - t0)
@@ -265,7 +267,7 @@ def workload_config(args, cfg, world):
                     f"{cfg['q']} latents and {cfg['p']} tasks per GPU",
         "n": n, "d": cfg["d"], "tasks_total": cfg["p"] * world, "latents_total": cfg["q"] * world,
         "latents_per_gpu": cfg["q"], "parallelism": f"latent-parallel x{world}",
-        "step": "MLL forward + full backward (no optimizer step)",
+        "step": "zero_grad + MLL forward + full backward + AdamW step + LR scheduler step (experiments.py:263-273)",
         "value_definition": "iterations/s of a 4-latent model of this shape; one step at N GPUs = N of them",
         "l2_policy": "inputs larger than L2 (K is %.1f GB per GPU)" % (cfg["q"] * n * n * 8 / 1e9),
     }
@@ -302,14 +304,18 @@ def main():
     Xd, Yd = model.train_inputs[0], model.train_y
     params = [prm for prm in model.parameters() if prm.requires_grad]
 
+    # optimiser and schedule of the reference's training loop (experiments.py:79-86, 240, 251, 263-273)
+    opt = torch.optim.AdamW(params, lr=1e-2)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=math.exp(math.log(1e-3 / 1e-2) / 10000))
+
     def step():
-        for prm in params:
-            prm.grad = None
+        opt.zero_grad(set_to_none=True)
         loss = -mll(model(Xd), Yd)
         loss.backward()
-        if world > 1:
-            return pdist.allreduce_loss_and_grads(loss, params)
-        return loss.detach()
+        loss = pdist.allreduce_loss_and_grads(loss, params) if world > 1 else loss.detach()
+        opt.step()
+        sched.step()
+        return loss
 
     def barrier():
         if world > 1:
