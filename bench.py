@@ -179,10 +179,10 @@ def roofline_entry(eng, achieved, dmma_peak, peaks, peak_src, gemm_flops, gemm_l
     }
     if s > 0:
         pairs = s * (s + 1) // 2
-        # potrf and trtri (2/3 of the q*n^3 FLOP) use s slices, lauum (1/3) fp64_slices_kinv: the roof is taken
-        # with the flop-weighted number of INT8 products per FP64 product
+        # potrf (1/3 of the q*n^3 FLOP) uses s slices, trtri + lauum (2/3; K^-1 feeds only the gradients)
+        # fp64_slices_kinv: the roof is taken with the flop-weighted number of INT8 products per FP64 product
         sk = min(getattr(eng, "fp64_slices_kinv", 0) or s, s)
-        pairs_eff = (2.0 * pairs + sk * (sk + 1) // 2) / 3.0
+        pairs_eff = (pairs + 2.0 * (sk * (sk + 1) // 2)) / 3.0
         bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
         peak = 2.0 * bf16 / pairs_eff
         common.update({
@@ -198,7 +198,7 @@ def roofline_entry(eng, achieved, dmma_peak, peaks, peak_src, gemm_flops, gemm_l
                       "gemm_dmma_kernel (DMMA.8x8x4) below" % (pairs, eng.fp64_min_dim),
             "peak": peak, "frac": (achieved / peak) if achieved else None,
             "peak_source": "2 x %s bf16 sustained (%.0f TFLOP/s) / %.2f INT8 products per FP64 product "
-                           "(%d slices in potrf/trtri, %d in lauum, flop-weighted)" % (peak_src, bf16, pairs_eff, s, sk),
+                           "(%d slices in potrf, %d in trtri/lauum, flop-weighted)" % (peak_src, bf16, pairs_eff, s, sk),
             "how": "algorithmic q*n^3 FLOP per step / CUDA-event time of the potrf+solve+potri phases",
         })
     else:

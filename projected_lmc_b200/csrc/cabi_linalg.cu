@@ -164,22 +164,9 @@ int plmc_solve_logdet(const double* L, long long ld, long long stride, long long
         n > npad || ldv < n || ldy < n)
         return PLMC_ERR_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const int gx = (int)((npad * 128 + 255) / 256 < 1184 ? (npad * 128 + 255) / 256 : 1184);
-    pack_rhs_kernel<<<dim3(gx, 1, batch), 256, 0, st>>>(y, ldy, rhs, n, npad);
-    PLMC_CHECK_LAUNCH();
-    LaCtx cx = make_ctx(st, batch);
-    BMat Lm{const_cast<double*>(L), ld, stride};
-    DinvBuf D{const_cast<double*>(dinv), npad * 128};
-    BMat R{rhs, 128, npad * 128};
-    trsm_lln(cx, Lm, (int)npad, D, 0, R, 128, 1.0);
-    if (cx.status) return cx.status;
-    const int gu = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
-    unpack_rhs_kernel<<<dim3(gu, 1, batch), 256, 0, st>>>(rhs, z, ldv, n, npad);
-    PLMC_CHECK_LAUNCH();
-    trsm_llt(cx, Lm, (int)npad, D, 0, R, 128, 1.0);
-    if (cx.status) return cx.status;
-    unpack_rhs_kernel<<<dim3(gu, 1, batch), 256, 0, st>>>(rhs, alpha, ldv, n, npad);
-    PLMC_CHECK_LAUNCH();
+    // two HBM-bound block substitutions on one vector (csrc/trsv.cu); rhs is the npad-vector workspace
+    const int rc = trsv_solve(L, ld, stride, dinv, npad * 128, y, ldy, rhs, npad * 128, z, alpha, ldv, n, npad, batch, st);
+    if (rc) return rc;
     quad_logdet_kernel<<<batch, 1024, 0, st>>>(z, ldv, L, ld, stride, n, quad, logdet);
     PLMC_CHECK_LAUNCH();
     note_launch(4);

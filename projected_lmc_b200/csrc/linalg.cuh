@@ -30,6 +30,10 @@ struct LaCtx {
     int oz_min = 1024;  // smallest M, N, K routed to the INT8 path
 };
 
+int trsv_solve(const double* L, long long ld, long long sL, const double* dinv, long long sD, const double* y,
+               long long ldy, double* v, long long sV, double* z, double* alpha, long long ldv, long long n,
+               long long npad, int batch, cudaStream_t st);
+
 void trace_enable(bool on);
 void trace_report();
 

@@ -65,10 +65,10 @@ class LatentEngine:
     # whole test-suite can be run in either mode.
     fp64_slices = int(__import__("os").environ.get("PLMC_FP64_SLICES", "7"))
     fp64_min_dim = int(__import__("os").environ.get("PLMC_FP64_MIN_DIM", "512"))
-    # slices for the LAUUM step of the training iteration (K^-1 = L^-T L^-1).  K^-1 feeds ONLY the gradient sweep
-    # tr((alpha alpha^T - K^-1) dK): the loss, alpha and the log-determinant come from L and L^-1, which keep
-    # fp64_slices.  47-bit products there perturb the gradients at the 1e-12 level (tolerance 1e-6) and save a
-    # quarter of the LAUUM time; 0 = same as fp64_slices.
+    # slices for the explicit inverse of the training iteration (K^-1 = L^-T L^-1: trtri + lauum).  K^-1 feeds ONLY
+    # the gradient sweep tr((alpha alpha^T - K^-1) dK): the loss, alpha and the log-determinant come from L, which
+    # keeps fp64_slices.  47-bit products there perturb the gradients at the 1e-13 level (tolerance 1e-6) and
+    # save a quarter of the time of those two steps; 0 = same as fp64_slices.
     fp64_slices_kinv = int(__import__("os").environ.get("PLMC_FP64_SLICES_KINV", "6"))
     _oz = None
 
@@ -157,11 +157,11 @@ class LatentEngine:
             z, alpha, quad, logdet = ops.solve_logdet(K, dinv, TY, n, ws["rhs"])
             mark("solve_logdet")
             return -0.5 * (quad + logdet + n * math.log(2 * math.pi)), None
-        # training step: the inverse factor is needed anyway, so the single-RHS solves
-        # become two HBM-bound triangular mat-vecs with L^-1 (no dependency chain)
-        ops.trtri(K, dinv)
-        mark("potri")
-        z, alpha, quad, logdet = ops.trmv_solve_logdet(K, TY, n, ws["rhs"])
+        # training step.  z, alpha, the quadratic form and the log-determinant come from L itself (two HBM-bound
+        # block substitutions, csrc/trsv.cu) at full FP64-grade accuracy.  The explicit inverse K^-1 = L^-T L^-1
+        # (trtri + lauum, 2/3 of the flops of the iteration) then feeds ONLY the gradient sweep
+        # tr((alpha alpha^T - K^-1) dK), so both steps may run with fp64_slices_kinv planes.
+        z, alpha, quad, logdet = ops.solve_logdet(K, dinv, TY, n, ws["rhs"])
         lp = -0.5 * (quad + logdet + n * math.log(2 * math.pi))
         mark("solve_logdet")
         s_kinv = min(self.fp64_slices_kinv, self.fp64_slices)
@@ -169,6 +169,7 @@ class LatentEngine:
         if lower:
             ops.set_fp64_emulation(self._oz, s_kinv, self.fp64_min_dim)
         try:
+            ops.trtri(K, dinv)
             ops.lauum(K)
         finally:
             if lower:
