@@ -87,8 +87,10 @@ int plmc_potrf_batched(double* K, long long ld, long long stride, long long npad
 int plmc_trsm_batched(int op, const double* L, long long ld, long long stride, long long npad, int batch,
                       const double* dinv, double* B, long long ldb, long long strideb, long long m, double alpha,
                       void* stream);
-/* rhs [batch, npad, 128] workspace.  Fills z = L^-1 y, alpha = L^-T z (both
- * [batch, ldv]), quad[b] = |z|^2, logdet[b] = 2 sum log L_ii.                   */
+/* rhs [batch, npad, 128] workspace (the first npad entries per member are used).
+ * Fills z = L^-1 y, alpha = L^-T z (both [batch, ldv]), quad[b] = |z|^2,
+ * logdet[b] = 2 sum log L_ii.  Two HBM-bound block substitutions: every tile of
+ * the lower triangle is read once per solve (csrc/trsv.cu).                     */
 int plmc_solve_logdet(const double* L, long long ld, long long stride, long long n, long long npad, int batch,
                       const double* dinv, const double* y, long long ldy, double* rhs, double* z, double* alpha,
                       long long ldv, double* quad, double* logdet, void* stream);

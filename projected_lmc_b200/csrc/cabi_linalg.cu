@@ -5,32 +5,6 @@ using namespace plmc;
 
 namespace plmc {
 
-// rhs[b, i, 0] = y[b, i] (i < n), everything else zero
-__global__ void pack_rhs_kernel(const double* __restrict__ y, long long ldy, double* __restrict__ rhs, long long n,
-                                long long npad) {
-    const int b = blockIdx.z;
-    const long long total = npad * 128;
-    double* R = rhs + (long long)b * total;
-    const double* Y = y + (long long)b * ldy;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const long long i = idx >> 7;
-        const int c = (int)(idx & 127);
-        R[idx] = (c == 0 && i < n) ? Y[i] : 0.0;
-    }
-}
-
-// out[b, i] = rhs[b, i, 0]
-__global__ void unpack_rhs_kernel(const double* __restrict__ rhs, double* __restrict__ out, long long ldv,
-                                  long long n, long long npad) {
-    const int b = blockIdx.z;
-    const double* R = rhs + (long long)b * npad * 128;
-    double* O = out + (long long)b * ldv;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x)
-        O[i] = R[i * 128];
-}
-
 // quad[b] = sum z_i^2 ; logdet[b] = 2 sum log L_ii   (fixed-order reduction)
 __global__ void __launch_bounds__(1024) quad_logdet_kernel(const double* __restrict__ z, long long ldv,
                                                             const double* __restrict__ L, long long ld,
