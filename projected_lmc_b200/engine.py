@@ -88,7 +88,18 @@ class LatentEngine:
         ops.set_fp64_emulation(self._oz, s, md)
 
     def release(self):
+        """Drop the HBM workspaces (and un-configure the INT8 path if it points at this engine's scratch)."""
         self._ws, self._ws_key = None, None
+        if self._oz is not None:
+            if ops._fp64_ws_ref is self._oz:
+                ops.set_fp64_emulation(None, 0, self.fp64_min_dim)
+            self._oz = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:   # interpreter shutdown: the library or torch may already be gone
+            pass
 
     def xmean(self, X: torch.Tensor) -> torch.Tensor:
         key = (X.data_ptr(), X._version, tuple(X.shape), str(X.device))

@@ -260,9 +260,18 @@ def ozaki_gemm(layout, A, B, C, M, N, K, alpha=1.0, beta=0.0, lower=False, slice
     return C
 
 
+_fp64_ws_ref = None   # keeps the scratch the library currently points at alive (the setting is process-wide)
+
+
 def set_fp64_emulation(ws, slices: int, min_dim: int = 1024):
-    """Route the large GEMMs of potrf/trsm/trtri/lauum through the tcgen05 INT8 path (slices=0: off)."""
+    """Route the large GEMMs of potrf/trsm/trtri/lauum through the tcgen05 INT8 path (slices=0: off).
+
+    The library stores the raw scratch pointer; this wrapper holds a reference to the tensor for as long as it
+    is the configured one, so an engine that goes away cannot leave the library writing into freed memory."""
+    global _fp64_ws_ref
     if ws is None or slices == 0:
         check(lib().plmc_set_fp64_emulation(None, 0, 0, max(128, min_dim)), "set_fp64_emulation")
+        _fp64_ws_ref = None
     else:
         check(lib().plmc_set_fp64_emulation(ptr(ws), ws.numel(), slices, max(128, min_dim)), "set_fp64_emulation")
+        _fp64_ws_ref = ws

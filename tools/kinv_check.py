@@ -20,7 +20,6 @@ for name, (s, sk) in {"dmma": (0, 0), "int8 7/7": (7, 7), "int8 7/6": (7, 6), "i
     loss.backward()
     out[name] = (loss.item(), torch.cat([p.grad.flatten() for p in m.parameters() if p.grad is not None]).cpu())
     m._engine.release()
-    m._engine._oz = None
     del m, loss
     import gc
     gc.collect()
