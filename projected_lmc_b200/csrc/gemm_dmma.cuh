@@ -300,24 +300,40 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(const GemmArgs 
 #endif
 
     // ---- epilogue ---------------------------------------------------------
+    // beta != 0: the old values of row group i + 1 are already in flight while group i is combined and stored
+    // (8 dependent load round trips per tile would otherwise rival the main loop of a K = 128 update)
     const double alpha = p.alpha, beta = p.beta;
+    auto cptr = [&](int i, int j) {
+        return reinterpret_cast<double2*>(C + (long long)(m0 + wm * 64 + i * 8 + g) * p.ldc + (n0 + wn * 32 + j * 8 + 2 * t));
+    };
+    if (beta != 0.0) {
+        double2 cn[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int row = m0 + wm * 64 + i * 8 + g;
+        for (int j = 0; j < 4; ++j) cn[j] = *cptr(0, j);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = n0 + wn * 32 + j * 8 + 2 * t;
-            double2* dst = reinterpret_cast<double2*>(C + (long long)row * p.ldc + col);
-            double2 o;
-            o.x = alpha * acc[i][j][0];
-            o.y = alpha * acc[i][j][1];
-            if (beta != 0.0) {
-                const double2 c = *dst;
-                o.x += beta * c.x;
-                o.y += beta * c.y;
+        for (int i = 0; i < 8; ++i) {
+            double2 c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = cn[j];
+            if (i + 1 < 8) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cn[j] = *cptr(i + 1, j);
             }
-            *dst = o;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double2 o;
+                o.x = alpha * acc[i][j][0];
+                o.y = alpha * acc[i][j][1];
+                o.x += beta * c[j].x;
+                o.y += beta * c[j].y;
+                *cptr(i, j) = o;
+            }
         }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *cptr(i, j) = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
     }
 }
 
