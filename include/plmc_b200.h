@@ -16,8 +16,15 @@
  *   - return value: 0 ok, -1 bad argument, -2 launch failure.  Numerical
  *     failure (non-PD matrix) is reported LAPACK-style in a device `info`
  *     array, never through the return code;
- *   - re-entrant; the only global state is one-time function attributes and the
- *     atomic launch counters behind plmc_stats_*;
+ *   - re-entrant: every numerical setting is a per-call argument (plmc_gemm_cfg).
+ *     The only process-wide state is (a) per-device one-time function attributes,
+ *     (b) the atomic launch counters behind plmc_stats_*, (c) the DIAGNOSTIC
+ *     switches plmc_trace_enable / plmc_ozaki_debug, which must not be toggled
+ *     while other threads are inside the library.  Calls on different streams,
+ *     from different threads, with different configurations and on different
+ *     devices (cudaSetDevice to the device that owns the buffers first) may run
+ *     concurrently as long as their buffers, including the plane scratch of
+ *     plmc_gemm_cfg, are distinct;
  *   - FP64 throughout; matrices row-major; "npad" = n rounded up to 128.
  */
 #ifndef PLMC_B200_H
@@ -32,8 +39,33 @@ extern "C" {
 #define PLMC_KERNEL_MATERN32 2 /* (1+sqrt3 r) exp(-sqrt3 r)               */
 #define PLMC_KERNEL_MATERN12 3 /* exp(-r)                                 */
 
+/* ---- arithmetic of the large GEMMs of the factorisation layer (per call) ----------------------
+ * FP64 matrix products with M, N and K all >= min_dim can be computed on the tcgen05 INT8 tensor
+ * path instead of the FP64 DMMA units (B200 has no FP64 kind on tcgen05):
+ *   PLMC_GEMM_INT8_DIGITS  operands split into `precision` (1..7) signed 8-bit digit planes, 8p-1 bits
+ *                          relative to the row/column maximum, p(p+1)/2 INT8 products (csrc/ozaki.cu);
+ *   PLMC_GEMM_INT8_RNS     operands scaled to integers and reduced modulo `precision` (8..18) pairwise
+ *                          coprime moduli <= 256; ONE INT8 product per modulus, exact integer result by
+ *                          the Chinese remainder theorem (csrc/ozaki2.cu).  16 moduli = 55 bits for
+ *                          K <= 16384 (plmc_rns_bits gives the bits for any K).
+ * A NULL cfg (or mode PLMC_GEMM_FP64) is pure FP64 arithmetic.  `ws` is caller-owned DEVICE scratch
+ * for the operand planes; a product that does not fit is processed in pieces (RNS) or falls back to
+ * the FP64 kernel (digits).  Two concurrent calls must not share `ws`.                            */
+#define PLMC_GEMM_FP64 0
+#define PLMC_GEMM_INT8_DIGITS 1
+#define PLMC_GEMM_INT8_RNS 2
+#define PLMC_GEMM_FLAG_SINGLE_CTA 1 /* RNS: 128x256 single-CTA tiles instead of CTA pairs (diagnostics) */
+typedef struct plmc_gemm_cfg {
+    void* ws;
+    long long ws_bytes;
+    int mode;
+    int precision;
+    int min_dim; /* >= 128 */
+    int flags;
+} plmc_gemm_cfg;
+
 int plmc_version(void);
-/* one-time per device: opt in to >48 KB dynamic shared memory for the kernels */
+/* optional: opt in to >48 KB dynamic shared memory on the current device (done lazily otherwise) */
 int plmc_init(void);
 /* host-side launch statistics since the last reset: kernels launched by this
  * library, GEMM launches among them, and their algorithmic FLOPs (2*M*N*K over the
@@ -82,11 +114,11 @@ int plmc_cross_gram(const double* Ztrain, const double* zntrain, const double* Z
 /* ---- (3) factorisation: MultivariateNormal.log_prob -> psd_safe_cholesky,
  * triangular solve, logdet (gpytorch; reached from projected_lmc.py:1201).     */
 int plmc_potrf_batched(double* K, long long ld, long long stride, long long npad, int batch, double* dinv, int* info,
-                       void* stream);
+                       const plmc_gemm_cfg* cfg, void* stream);
 /* op: 0 X L^T = aB (B m x npad) | 1 X L = aB | 2 L X = aB (B npad x m) | 3 L^T X = aB ; m % 128 == 0 */
 int plmc_trsm_batched(int op, const double* L, long long ld, long long stride, long long npad, int batch,
                       const double* dinv, double* B, long long ldb, long long strideb, long long m, double alpha,
-                      void* stream);
+                      const plmc_gemm_cfg* cfg, void* stream);
 /* rhs [batch, npad, 128] workspace (the first npad entries per member are used).
  * Fills z = L^-1 y, alpha = L^-T z (both [batch, ldv]), quad[b] = |z|^2,
  * logdet[b] = 2 sum log L_ii.  Two HBM-bound block substitutions: every tile of
@@ -94,22 +126,15 @@ int plmc_trsm_batched(int op, const double* L, long long ld, long long stride, l
 int plmc_solve_logdet(const double* L, long long ld, long long stride, long long n, long long npad, int batch,
                       const double* dinv, const double* y, long long ldy, double* rhs, double* z, double* alpha,
                       long long ldv, double* quad, double* logdet, void* stream);
-/* The same four outputs from the EXPLICIT inverse factor (training step: trtri has
- * already run): z = Linv y, alpha = Linv^T z, quad, logdet = -2 sum log Linv_ii.
- * Two HBM passes over the lower triangle instead of two blocked solves.
- * ws: plmc_trmv_ws(npad, batch) bytes.                                           */
-long long plmc_trmv_ws(long long npad, int batch);
-int plmc_trmv_solve_logdet(const double* Linv, long long ld, long long stride, long long n, long long npad,
-                           int batch, const double* y, long long ldy, double* ws, double* z, double* alpha,
-                           long long ldv, double* quad, double* logdet, void* stream);
 /* L -> inv(L) (lower) in place */
 int plmc_trtri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
-                       void* stream);
+                       const plmc_gemm_cfg* cfg, void* stream);
 /* L -> lower(L^T L) in place */
-int plmc_lauum_batched(double* L, long long ld, long long stride, long long npad, int batch, void* stream);
+int plmc_lauum_batched(double* L, long long ld, long long stride, long long npad, int batch,
+                       const plmc_gemm_cfg* cfg, void* stream);
 /* L -> lower(K^-1) in place = trtri + lauum */
 int plmc_potri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
-                       void* stream);
+                       const plmc_gemm_cfg* cfg, void* stream);
 
 /* ---- (4) fused backward: autograd of log_prob through the kernel
  * (experiments.py:270 loss.backward()).  With W = 1/2 (alpha alpha^T - K^-1):
@@ -148,11 +173,6 @@ int plmc_gemm(int layout, const double* A, long long lda, long long sA, const do
  * reproduce a DGEMM to its own rounding level.  same_operand != 0: op(B)^T is op(A) (SYRK),
  * sliced once.  ws: plmc_ozaki_ws_bytes(...) bytes of scratch.                                */
 long long plmc_ozaki_ws_bytes(int M, int N, int K, int slices, int same_operand);
-/* Route every GEMM of the blocked factorisation layer (potrf / trsm / trtri / lauum) whose M, N
- * and K are all >= min_dim through the INT8 path with `slices` planes, using the caller-owned
- * scratch `ws` (a GEMM whose planes do not fit falls back to the DMMA kernel).  slices = 0
- * switches the emulation off (pure FP64 DMMA arithmetic).  Process-wide setting.              */
-int plmc_set_fp64_emulation(void* ws, long long ws_bytes, int slices, int min_dim);
 /* diagnostics: with a device buffer of 64 x 8 int64 set, CTA 0 of every later INT8 GEMM launch records
  * clock64 stamps per tile (0 MMA start, 1 last MMA issued, 2 accumulators complete, 3 TMEM drained,
  * 4 C written, 5/6 first/last copy issued); NULL switches it off.                                  */
@@ -161,10 +181,29 @@ int plmc_ozaki_gemm(int layout, const double* A, long long lda, const double* B,
                     long long ldc, int M, int N, int K, double alpha, double beta, int lower, int slices,
                     int same_operand, void* ws, long long ws_bytes, void* stream);
 
+/* ---- FP64 GEMM on the tcgen05 INT8 tensor path, residue-number-system scheme (csrc/ozaki2.cu):
+ * C = alpha op(A) op(B) + beta C for ONE matrix; M, N, K multiples of 128.  `moduli` (8..18) INT8
+ * products (one per modulus, CTA-pair tcgen05.mma.cta_group::2 kernel) + Chinese-remainder
+ * reconstruction in FP64.  plmc_rns_bits: operand bits relative to the row (column) maximum for an
+ * inner dimension K (2 K 4^bits < product of the moduli).  ws: >= plmc_rns_ws_bytes(...) gives one
+ * pass; a smaller scratch makes the call split the product.  flags: PLMC_GEMM_FLAG_*.            */
+int plmc_rns_bits(int moduli, int K);
+long long plmc_rns_ws_bytes(int M, int N, int K, int moduli, int same_operand, int lower);
+/* host-only helper (no device work): moduli p_i, the leading 40 bits H_i and the tail L_i of
+ * ((P/p_i)^-1 mod p_i) / p_i, pscale = P 2^(-2 bits) and the operand bits for (moduli, K).        */
+int plmc_rns_constants(int moduli, int K, int* moduli_out, double* H, double* L, double* pscale, int* bits);
+int plmc_rns_gemm(int layout, const double* A, long long lda, const double* B, long long ldb, double* C,
+                  long long ldc, int M, int N, int K, double alpha, double beta, int lower, int moduli,
+                  int same_operand, void* ws, long long ws_bytes, int flags, void* stream);
+
 /* ---- roofline denominators (time with CUDA events on `stream`) */
 int plmc_peak_dmma(int blocks, int threads, long long iters, double* scratch, void* stream);
 int plmc_peak_dfma(int blocks, int threads, long long iters, double* scratch, void* stream);
 int plmc_peak_copy(const double* src, double* dst, long long n, void* stream);
+/* INT8 tensor-pipe peak: every SM (cta_group 1) or SM pair (cta_group 2) issues iters x 4
+ * tcgen05.mma.kind::i8 of 128(256) x 256 x 32 on shared-memory-resident operands; *ops_host (HOST
+ * pointer) receives the INT8 operations (2 per MAC) of the launch.  scratch is unused.          */
+int plmc_peak_i8(long long iters, int cta_group, void* scratch, double* ops_host, void* stream);
 /* even warps run the DMMA loop (iters_mma x 16 x 512 FLOP per warp), odd warps the DFMA loop
  * (iters_fma x 16 x 2 FLOP per thread): shows that on B200 the two share one FP64 datapath
  * (measured sum 35-36 TFLOP/s for every mix), i.e. 37 TFLOP/s is the FP64 roof.          */

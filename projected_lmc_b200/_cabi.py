@@ -18,6 +18,18 @@ _inited_devices = set()
 
 P, LL, I, D = c_void_p, c_longlong, c_int, c_double
 
+GEMM_FP64, GEMM_INT8_DIGITS, GEMM_INT8_RNS = 0, 1, 2
+GEMM_FLAG_SINGLE_CTA = 1
+
+
+class GemmCfg(ctypes.Structure):
+    """plmc_gemm_cfg (include/plmc_b200.h): per-call arithmetic of the large GEMMs of the factorisation layer."""
+    _fields_ = [("ws", c_void_p), ("ws_bytes", c_longlong), ("mode", c_int), ("precision", c_int),
+                ("min_dim", c_int), ("flags", c_int)]
+
+
+CFG = ctypes.POINTER(GemmCfg)
+
 # name -> argtypes (restype is int unless listed in _RET_LL)
 _SIGNATURES = {
     "plmc_version": [],
@@ -36,14 +48,12 @@ _SIGNATURES = {
     "plmc_scale_inputs": [P, P, P, P, P, LL, I, I, LL, I, P],
     "plmc_gram": [P, P, I, P, P, P, LL, LL, LL, LL, I, I, P],
     "plmc_cross_gram": [P, P, P, P, I, P, P, LL, LL, LL, LL, LL, LL, I, I, P],
-    "plmc_potrf_batched": [P, LL, LL, LL, I, P, P, P],
-    "plmc_trsm_batched": [I, P, LL, LL, LL, I, P, P, LL, LL, LL, D, P],
+    "plmc_potrf_batched": [P, LL, LL, LL, I, P, P, CFG, P],
+    "plmc_trsm_batched": [I, P, LL, LL, LL, I, P, P, LL, LL, LL, D, CFG, P],
     "plmc_solve_logdet": [P, LL, LL, LL, LL, I, P, P, LL, P, P, P, LL, P, P, P],
-    "plmc_trmv_ws": [LL, I],
-    "plmc_trmv_solve_logdet": [P, LL, LL, LL, LL, I, P, LL, P, P, P, LL, P, P, P],
-    "plmc_trtri_batched": [P, LL, LL, LL, I, P, P],
-    "plmc_lauum_batched": [P, LL, LL, LL, I, P],
-    "plmc_potri_batched": [P, LL, LL, LL, I, P, P],
+    "plmc_trtri_batched": [P, LL, LL, LL, I, P, CFG, P],
+    "plmc_lauum_batched": [P, LL, LL, LL, I, CFG, P],
+    "plmc_potri_batched": [P, LL, LL, LL, I, P, CFG, P],
     "plmc_grad_ws": [LL, I, I],
     "plmc_grad_sweep": [P, LL, LL, P, LL, P, P, P, I, P, P, P, P, P, LL, LL, I, I, I, P],
     "plmc_latent_mean": [P, LL, LL, P, LL, P, LL, LL, LL, I, P],
@@ -51,14 +61,19 @@ _SIGNATURES = {
     "plmc_mix_tasks": [P, P, LL, P, P, P, P, LL, I, I, I, P],
     "plmc_gemm": [I, P, LL, LL, P, LL, LL, P, LL, LL, I, I, I, D, D, I, I, I, I, P],
     "plmc_ozaki_ws_bytes": [I, I, I, I, I],
-    "plmc_set_fp64_emulation": [P, LL, I, I],
+    "plmc_rns_bits": [I, I],
+    "plmc_rns_ws_bytes": [I, I, I, I, I, I],
+    "plmc_rns_constants": [I, I, P, P, P, P, P],
+    "plmc_peak_i8": [LL, I, P, P, P],
+    "plmc_rns_gemm": [I, P, LL, P, LL, P, LL, I, I, I, D, D, I, I, I, P, LL, I, P],
     "plmc_ozaki_gemm": [I, P, LL, P, LL, P, LL, I, I, I, D, D, I, I, I, P, LL, P],
     "plmc_peak_dmma": [I, I, LL, P, P],
     "plmc_peak_dfma": [I, I, LL, P, P],
     "plmc_peak_copy": [P, P, LL, P],
     "plmc_peak_mixed": [I, I, LL, LL, P, P],
 }
-_RET_LL = {"plmc_npad", "plmc_dinv_bytes", "plmc_project_bwd_ws", "plmc_grad_ws", "plmc_trmv_ws", "plmc_ozaki_ws_bytes"}
+_RET_LL = {"plmc_npad", "plmc_dinv_bytes", "plmc_project_bwd_ws", "plmc_grad_ws", "plmc_ozaki_ws_bytes",
+           "plmc_rns_ws_bytes"}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -93,17 +108,28 @@ def load():
 
 
 def lib():
-    """Library handle ready for device calls on the current CUDA device."""
+    """Library handle ready for device calls (function attributes are set lazily per device inside the library)."""
     l = load()
     if not torch.cuda.is_available():
         raise PlmcError("projected_lmc_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
-    dev = torch.cuda.current_device()
-    if dev not in _inited_devices:
-        rc = l.plmc_init()
-        if rc != 0:
-            raise PlmcError(f"plmc_init failed with {rc} (is this an sm_100a device?)")
-        _inited_devices.add(dev)
     return l
+
+
+def device_of(*tensors):
+    """Context manager making the device of the given tensors current for the duration of a library call
+    (the library launches on the current device; a tensor on another GPU would otherwise be launched on the
+    wrong device's stream)."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise PlmcError("libplmc_b200 was handed a non-CUDA tensor; there is no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise PlmcError(f"libplmc_b200 call with tensors on different devices: {dev} and {t.device}")
+    return torch.cuda.device(dev)
 
 
 def check(rc: int, what: str = "") -> None:

@@ -30,33 +30,33 @@ __global__ void __launch_bounds__(1024) quad_logdet_kernel(const double* __restr
 
 }  // namespace plmc
 
-// FP64-emulation configuration (process-wide; one process per GPU)
-static void* g_oz_ws = nullptr;
-static long long g_oz_bytes = 0;
-static int g_oz_slices = 0;
-static int g_oz_min = 1024;
+#include "plmc_b200.h"
 
-static LaCtx make_ctx(cudaStream_t st, int batch) {
-    LaCtx cx{st, batch, 0};
-    cx.oz_ws = g_oz_ws;
-    cx.oz_bytes = g_oz_bytes;
-    cx.oz_slices = g_oz_slices;
-    cx.oz_min = g_oz_min;
-    return cx;
+// The arithmetic of the large GEMMs is a PER-CALL argument (plmc_gemm_cfg): no process-wide setting.
+// Returns false for an inconsistent configuration.
+static bool make_ctx(LaCtx& cx, cudaStream_t st, int batch, const plmc_gemm_cfg* cfg) {
+    cx = LaCtx{st, batch, 0};
+    if (!cfg || cfg->mode == PLMC_GEMM_FP64) return true;
+    if (cfg->mode == PLMC_GEMM_INT8_DIGITS) {
+        if (cfg->precision < 1 || cfg->precision > 7) return false;
+    } else if (cfg->mode == PLMC_GEMM_INT8_RNS) {
+        if (cfg->precision < 8 || cfg->precision > 18) return false;
+    } else {
+        return false;
+    }
+    if (!cfg->ws || cfg->ws_bytes <= 0 || cfg->min_dim < 128) return false;
+    cx.oz_ws = cfg->ws;
+    cx.oz_bytes = cfg->ws_bytes;
+    cx.oz_mode = cfg->mode;
+    cx.oz_prec = cfg->precision;
+    cx.oz_min = cfg->min_dim;
+    cx.oz_flags = cfg->flags;
+    return true;
 }
 
 extern "C" {
 
 int plmc_version(void) { return 100; }
-
-int plmc_set_fp64_emulation(void* ws, long long ws_bytes, int slices, int min_dim) {
-    if (slices < 0 || slices > 7 || (slices > 0 && (!ws || ws_bytes <= 0)) || min_dim < 128) return PLMC_ERR_BADARG;
-    g_oz_ws = ws;
-    g_oz_bytes = ws_bytes;
-    g_oz_slices = slices;
-    g_oz_min = min_dim;
-    return PLMC_OK;
-}
 
 int plmc_trace_enable(int on) {
     trace_enable(on != 0);
@@ -104,20 +104,22 @@ static bool bad_mat(const void* p, long long ld, long long npad, int batch) {
 }
 
 int plmc_potrf_batched(double* K, long long ld, long long stride, long long npad, int batch, double* dinv, int* info,
-                       void* stream) {
+                       const plmc_gemm_cfg* cfg, void* stream) {
     if (bad_mat(K, ld, npad, batch) || !dinv || !info) return PLMC_ERR_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
+    LaCtx cx;
+    if (!make_ctx(cx, st, batch, cfg)) return PLMC_ERR_BADARG;
     if (cudaMemsetAsync(info, 0, sizeof(int) * batch, st) != cudaSuccess) return PLMC_ERR_LAUNCH;
-    LaCtx cx = make_ctx(st, batch);
     potrf_lower(cx, BMat{K, ld, stride}, (int)npad, DinvBuf{dinv, npad * 128}, 0, info);
     return cx.status;
 }
 
 int plmc_trsm_batched(int op, const double* L, long long ld, long long stride, long long npad, int batch,
                       const double* dinv, double* B, long long ldb, long long strideb, long long m, double alpha,
-                      void* stream) {
+                      const plmc_gemm_cfg* cfg, void* stream) {
     if (bad_mat(L, ld, npad, batch) || !dinv || !B || m <= 0 || (m % 128) || (ldb & 1)) return PLMC_ERR_BADARG;
-    LaCtx cx = make_ctx((cudaStream_t)stream, batch);
+    LaCtx cx;
+    if (!make_ctx(cx, (cudaStream_t)stream, batch, cfg)) return PLMC_ERR_BADARG;
     BMat Lm{const_cast<double*>(L), ld, stride};
     DinvBuf D{const_cast<double*>(dinv), npad * 128};
     BMat Bm{B, ldb, strideb};
@@ -148,24 +150,27 @@ int plmc_solve_logdet(const double* L, long long ld, long long stride, long long
 }
 
 int plmc_trtri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
-                       void* stream) {
+                       const plmc_gemm_cfg* cfg, void* stream) {
     if (bad_mat(L, ld, npad, batch) || !dinv) return PLMC_ERR_BADARG;
-    LaCtx cx = make_ctx((cudaStream_t)stream, batch);
+    LaCtx cx;
+    if (!make_ctx(cx, (cudaStream_t)stream, batch, cfg)) return PLMC_ERR_BADARG;
     trtri_lower(cx, BMat{L, ld, stride}, (int)npad, DinvBuf{const_cast<double*>(dinv), npad * 128}, 0);
     return cx.status;
 }
 
-int plmc_lauum_batched(double* L, long long ld, long long stride, long long npad, int batch, void* stream) {
+int plmc_lauum_batched(double* L, long long ld, long long stride, long long npad, int batch,
+                       const plmc_gemm_cfg* cfg, void* stream) {
     if (bad_mat(L, ld, npad, batch)) return PLMC_ERR_BADARG;
-    LaCtx cx = make_ctx((cudaStream_t)stream, batch);
+    LaCtx cx;
+    if (!make_ctx(cx, (cudaStream_t)stream, batch, cfg)) return PLMC_ERR_BADARG;
     lauum_lower(cx, BMat{L, ld, stride}, (int)npad);
     return cx.status;
 }
 
 int plmc_potri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
-                       void* stream) {
-    int r = plmc_trtri_batched(L, ld, stride, npad, batch, dinv, stream);
+                       const plmc_gemm_cfg* cfg, void* stream) {
+    int r = plmc_trtri_batched(L, ld, stride, npad, batch, dinv, cfg, stream);
     if (r) return r;
-    return plmc_lauum_batched(L, ld, stride, npad, batch, stream);
+    return plmc_lauum_batched(L, ld, stride, npad, batch, cfg, stream);
 }
 }

@@ -61,8 +61,21 @@ static void launch_variant(bool aKC, bool bKC, dim3 grid, cudaStream_t st, const
         gemm_dmma_kernel<false, false, T><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
 }
 
+// the >48 KB shared-memory opt-in is a per-device function attribute: done lazily, once per device ordinal
+static bool g_gemm_attr_done[64];
+static int gemm_attrs_for_current_device() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PLMC_ERR_LAUNCH;
+    if (!g_gemm_attr_done[dev]) {
+        if (gemm_init_attrs() != PLMC_OK) return PLMC_ERR_LAUNCH;
+        g_gemm_attr_done[dev] = true;
+    }
+    return PLMC_OK;
+}
+
 int gemm_launch(bool aKC, bool bKC, const GemmArgs& a, int batch, cudaStream_t st) {
     if (a.M <= 0 || a.N <= 0 || batch <= 0) return PLMC_OK;
+    if (int rc = gemm_attrs_for_current_device()) return rc;
     if (a.M % G_BM || a.N % G_BN || a.K % G_BK || a.K <= 0) return PLMC_ERR_BADARG;
     if ((a.lda & 1) || (a.ldb & 1) || (a.ldc & 1)) return PLMC_ERR_BADARG;
     const long long tm = a.M / G_BM, tn = a.N / G_BN;

@@ -20,13 +20,22 @@ __global__ void dinv_to_diag_kernel(double* __restrict__ Lbase, long long ld, lo
     }
 }
 
-static bool g_leaf_attr_done = false;
+int current_device() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= PLMC_MAX_DEVICES) return -1;
+    return dev;
+}
+
+// function attributes are per device: one flag per device ordinal (idempotent, so a race only repeats the call)
+static bool g_leaf_attr_done[PLMC_MAX_DEVICES];
 static int leaf_attr() {
-    if (!g_leaf_attr_done) {
+    const int dev = current_device();
+    if (dev < 0) return PLMC_ERR_LAUNCH;
+    if (!g_leaf_attr_done[dev]) {
         if (cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM) !=
             cudaSuccess)
             return PLMC_ERR_LAUNCH;
-        g_leaf_attr_done = true;
+        g_leaf_attr_done[dev] = true;
     }
     return PLMC_OK;
 }
@@ -82,13 +91,19 @@ void trace_report() {
 static void gemm_impl(LaCtx& cx, bool aKC, bool bKC, BMat A, BMat B, BMat C, int M, int N, int K, double alpha,
                       double beta, int lower, int triA, int triB, int* path) {
     if (cx.status) return;
-    if (cx.oz_slices > 0 && !triA && !triB && M >= cx.oz_min && N >= cx.oz_min && K >= cx.oz_min) {
+    if (cx.oz_mode > 0 && cx.oz_prec > 0 && !triA && !triB && M >= cx.oz_min && N >= cx.oz_min && K >= cx.oz_min) {
         // large update: FP64 product through the INT8 tensor path (all batch members per launch when
         // the plane scratch holds them, otherwise in passes; everything is ordered on the one stream)
         const bool same = (A.p == B.p && A.ld == B.ld && aKC == bKC && M == N);
-        if (ozaki_ws_bytes(M, N, K, cx.oz_slices, same) + 1024 <= cx.oz_bytes) {
+        if (cx.oz_mode == 2) {   // residue planes: a product that does not fit the scratch is split inside
+            cx.status = rns_gemm(aKC, bKC, A.p, A.ld, A.stride, B.p, B.ld, B.stride, C.p, C.ld, C.stride, M, N, K, alpha,
+                                 beta, lower, cx.oz_prec, same, cx.batch, cx.oz_ws, cx.oz_bytes, cx.oz_flags, cx.st);
+            *path = 1;
+            return;
+        }
+        if (ozaki_ws_bytes(M, N, K, cx.oz_prec, same) + 1024 <= cx.oz_bytes) {
             cx.status = ozaki_gemm(aKC, bKC, A.p, A.ld, A.stride, B.p, B.ld, B.stride, C.p, C.ld, C.stride, M, N, K,
-                                   alpha, beta, lower, cx.oz_slices, same, cx.batch, cx.oz_ws, cx.oz_bytes, cx.st);
+                                   alpha, beta, lower, cx.oz_prec, same, cx.batch, cx.oz_ws, cx.oz_bytes, cx.st);
             *path = 1;
             return;
         }

@@ -23,12 +23,20 @@ struct LaCtx {
     cudaStream_t st;
     int batch;
     int status;  // first non-zero launch status
-    // FP64-via-INT8 (tcgen05, csrc/ozaki.cu) for the large GEMMs of the recursion; 0 slices = off
+    // FP64 through the INT8 tensor path (tcgen05) for the large GEMMs of the recursion (plmc_gemm_cfg):
+    // mode 0 = off (DMMA only), 1 = digit planes (csrc/ozaki.cu, oz_prec slices), 2 = residue planes
+    // (csrc/ozaki2.cu, oz_prec moduli)
     void* oz_ws = nullptr;
     long long oz_bytes = 0;
-    int oz_slices = 0;
+    int oz_mode = 0;
+    int oz_prec = 0;
     int oz_min = 1024;  // smallest M, N, K routed to the INT8 path
+    int oz_flags = 0;   // bit 0: single-CTA kernel in mode 2
 };
+
+// per-device one-time state (function attributes, SM count): indexed by the CUDA device ordinal
+constexpr int PLMC_MAX_DEVICES = 64;
+int current_device();   // -1 on failure
 
 int trsv_solve(const double* L, long long ld, long long sL, const double* dinv, long long sD, const double* y,
                long long ldy, double* v, long long sV, double* z, double* alpha, long long ldv, long long n,
@@ -41,6 +49,13 @@ long long ozaki_ws_bytes(int M, int N, int K, int s, bool same_operand);
 int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA, const double* B, long long ldb,
                long long sB, double* C, long long ldc, long long sC, int M, int N, int K, double alpha, double beta,
                int lower, int s, bool same_operand, int batch, void* ws, long long ws_bytes, cudaStream_t st);
+
+int rns_bits(int nmod, int K);
+long long rns_ws_bytes(int M, int N, int K, int nmod, bool same_operand, bool lower);
+int rns_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA, const double* B, long long ldb,
+             long long sB, double* C, long long ldc, long long sC, int M, int N, int K, double alpha, double beta,
+             int lower, int nmod, bool same_operand, int batch, void* ws, long long ws_bytes, int flags,
+             cudaStream_t st);
 
 // Dinv: per batch member, n/128 consecutive 128x128 row-major blocks holding
 // inv(L_kk) (upper part explicitly zero).  stride = (n/128)*16384.

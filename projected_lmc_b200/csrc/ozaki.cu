@@ -30,7 +30,7 @@
 // quarter).  s accumulators (one per diagonal g, 64 TMEM columns each, 448 of 512 columns at s = 7).  All pairs (i, j) of one A plane i are a
 // single wide MMA: their accumulators g = i..s-1 are consecutive TMEM column blocks and the
 // B planes consecutive shared-memory row blocks, so A_i is read from shared memory once.
-#include "plmc_common.cuh"
+#include "linalg.cuh"
 
 namespace plmc {
 
@@ -573,9 +573,9 @@ __global__ void __launch_bounds__(256) slice_mc_kernel(const double* __restrict_
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-static bool g_oz_attr = false;
-static long long* g_oz_dbg = nullptr;
-static int g_oz_sms = 148;   // CTAs of the persistent kernel (one per SM)
+static bool g_oz_attr[PLMC_MAX_DEVICES];   // per device: opt-in shared memory of the kernel set, SM count read
+static int g_oz_sms_dev[PLMC_MAX_DEVICES];
+static long long* g_oz_dbg = nullptr;      // diagnostics only (plmc_ozaki_debug)
 
 // scratch for ONE batch member (tile images of both operands + exponents)
 long long ozaki_ws_bytes(int M, int N, int K, int s, bool same_operand) {
@@ -601,18 +601,20 @@ int ozaki_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA,
     const int bc_max = (int)((avail / need1) < batch ? (avail / need1) : batch);
     const long long bytesA = (long long)s * M * K;                       // multiple of 4096
     const long long bytesB = same_operand ? 0 : (long long)s * N * K;
-    if (!g_oz_attr) {
+    const int dev = current_device();
+    if (dev < 0) return PLMC_ERR_LAUNCH;
+    if (!g_oz_attr[dev]) {
         int smem_max = 0;
         for (int t = 1; t <= OZ_SMAX; ++t) smem_max = oz_smem_bytes(t) > smem_max ? oz_smem_bytes(t) : smem_max;
         if (cudaFuncSetAttribute(ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max) !=
             cudaSuccess)
             return PLMC_ERR_LAUNCH;
-        int dev = 0, sms = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
-            g_oz_sms = sms;
-        g_oz_attr = true;
+        int sms = 0;
+        g_oz_sms_dev[dev] =
+            (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) ? sms : 148;
+        g_oz_attr[dev] = true;
     }
+    const int g_oz_sms = g_oz_sms_dev[dev];
     const int smem = oz_smem_bytes(s);
 
     for (int b0 = 0; b0 < batch; b0 += bc_max) {

@@ -34,12 +34,21 @@ class NanError(RuntimeError):
 
 
 class LatentEngine:
+    """Per-model device orchestration.  All numerical settings travel with each library call (plmc_gemm_cfg);
+    nothing here touches process-wide state, so engines with different settings may run concurrently on
+    different streams or devices."""
+
     def __init__(self):
         self._ws = None
         self._ws_key = None
         self._xmean = None
         self._xmean_key = None
+        self._oz = None
+        self._cfg = (None, None)
+        self._cfg_key = None
+        self._pinned = None
         self.last_jitter = None
+        self.generation = 0     # bumped whenever ws['K'] is rewritten (prediction caches compare it)
 
     # -- workspaces -----------------------------------------------------------
     def workspace(self, device, q: int, n: int):
@@ -51,55 +60,89 @@ class LatentEngine:
                 K=torch.empty((q, np_, np_), dtype=torch.float64, device=device),
                 dinv=ops.alloc_dinv(np_, q, device),
                 rhs=torch.empty((q, np_, 128), dtype=torch.float64, device=device),
-                info=torch.zeros((q,), dtype=torch.int32, device=device),
+                info=torch.zeros((q + 1,), dtype=torch.int32, device=device),   # [q] = non-finite-input flag
             )
             self._ws_key = key
-            self._oz = None
+            self._oz, self._cfg_key = None, None
         self._configure_fp64(device, np_, q)
         return self._ws
 
-    # -- FP64 through the INT8 tensor path (csrc/ozaki.cu) for the large GEMMs ------------------
-    # slices: number of signed 8-bit planes per operand, 8*slices-1 bits (7: DGEMM-grade rounding,
-    # 6: 47 bits and ~14 % faster; 0 = pure DMMA arithmetic); min_dim: smallest
-    # GEMM dimension routed to the INT8 path.  Defaults come from the environment so that the
-    # whole test-suite can be run in either mode.
+    # -- FP64 through the INT8 tensor path for the large GEMMs ----------------------------------------
+    # gemm_mode: "rns"    residue planes (csrc/ozaki2.cu): rns_moduli INT8 products per FP64 product
+    #                     (16 = 55 operand bits for K <= 16384, DGEMM-grade; 14 = 47 bits);
+    #            "digits" 8-bit digit planes (csrc/ozaki.cu): fp64_slices planes, s(s+1)/2 products
+    #                     (7 = 55 bits, 6 = 47 bits);
+    #            "fp64"   pure DMMA arithmetic (also selected by fp64_slices = 0 / PLMC_FP64_SLICES=0).
+    # fp64_min_dim: smallest GEMM dimension routed to the INT8 path.  Defaults come from the environment so
+    # that the whole test-suite can be run in any mode.
+    gemm_mode = __import__("os").environ.get("PLMC_GEMM_MODE", "rns")
     fp64_slices = int(__import__("os").environ.get("PLMC_FP64_SLICES", "7"))
     fp64_min_dim = int(__import__("os").environ.get("PLMC_FP64_MIN_DIM", "512"))
-    # slices for the explicit inverse of the training iteration (K^-1 = L^-T L^-1: trtri + lauum).  K^-1 feeds ONLY
-    # the gradient sweep tr((alpha alpha^T - K^-1) dK): the loss, alpha and the log-determinant come from L, which
-    # keeps fp64_slices.  47-bit products there perturb the gradients at the 1e-13 level (tolerance 1e-6) and
-    # save a quarter of the time of those two steps; 0 = same as fp64_slices.
+    rns_moduli = int(__import__("os").environ.get("PLMC_RNS_MODULI", "16"))
+    # precision of the explicit inverse of the training iteration (K^-1 = L^-T L^-1: trtri + lauum).  K^-1 feeds
+    # ONLY the gradient sweep tr((alpha alpha^T - K^-1) dK): the loss, alpha and the log-determinant come from L,
+    # which keeps the full precision.  47-bit products there perturb the gradients at the 1e-13 level
+    # (tolerance 1e-6) and save a quarter (digits) / an eighth (rns) of those two steps; 0 = same as the main one.
     fp64_slices_kinv = int(__import__("os").environ.get("PLMC_FP64_SLICES_KINV", "6"))
-    _oz = None
+    rns_moduli_kinv = int(__import__("os").environ.get("PLMC_RNS_MODULI_KINV", "14"))
+    rns_flags = int(__import__("os").environ.get("PLMC_RNS_FLAGS", "0"))
+    scratch_cap_bytes = int(float(__import__("os").environ.get("PLMC_SCRATCH_GB", "48")) * (1 << 30))
+
+    def emulation_mode(self):
+        if self.fp64_slices <= 0 or self.gemm_mode == "fp64":
+            return "fp64"
+        return "rns" if self.gemm_mode == "rns" else "digits"
 
     def _configure_fp64(self, device, np_, q=1):
-        s, md = self.fp64_slices, self.fp64_min_dim
-        if s <= 0 or np_ < 2 * md:
-            ops.set_fp64_emulation(None, 0, md)
+        mode, md = self.emulation_mode(), self.fp64_min_dim
+        key = (mode, md, self.fp64_slices, self.fp64_slices_kinv, self.rns_moduli, self.rns_moduli_kinv,
+               self.rns_flags, str(device), np_, q)
+        if key == self._cfg_key:
             return
-        # planes of the largest GEMM of the recursion (s * (M + N) * K bytes, M, K <= npad/2, N <= npad/2
-        # or a prediction tile) for every latent, capped: the library works through the batch in passes
-        # when the scratch holds fewer members
-        per_member = s * (np_ // 2) * (np_ // 2 + 8192) + (1 << 20)
-        need = min(q * per_member, max(per_member, 24 << 30))
+        self._cfg_key = key
+        if mode == "fp64" or np_ < 2 * md:
+            self._cfg = (None, None)
+            return
+        h = np_ // 2
+        if mode == "rns":
+            # planes + residue tiles of the largest product of the recursion (the top-level SYRK) per latent;
+            # a product that does not fit is split inside the library, batch members are processed in passes
+            m = self.rns_moduli
+            per_member = m * h * h + m * (h + 256) * (h + 256) // 2 + m * h * 8192 + (1 << 20)
+        else:
+            # digit planes of the largest GEMM (s * (M + N) * K bytes, M, K <= npad/2, N <= npad/2 or a
+            # prediction tile); a GEMM whose planes do not fit falls back to the DMMA kernel
+            per_member = self.fp64_slices * h * (h + 8192) + (1 << 20)
+        cap = self.scratch_cap_bytes
+        if device.type == "cuda":
+            free, _ = torch.cuda.mem_get_info(device)
+            have = self._oz.numel() if self._oz is not None and self._oz.device == device else 0
+            cap = max(per_member // 8, min(cap, free + have - (6 << 30)))
+        need = int(min(q * per_member, max(cap, 1 << 26)))
         if self._oz is None or self._oz.numel() < need or self._oz.device != device:
             self._oz = None
             self._oz = torch.empty((need,), dtype=torch.uint8, device=device)
-        ops.set_fp64_emulation(self._oz, s, md)
+        if mode == "rns":
+            mk = min(self.rns_moduli_kinv or self.rns_moduli, self.rns_moduli)
+            self._cfg = (ops.gemm_cfg(self._oz, ops.GEMM_INT8_RNS, self.rns_moduli, md, self.rns_flags),
+                         ops.gemm_cfg(self._oz, ops.GEMM_INT8_RNS, mk, md, self.rns_flags))
+        else:
+            sk = min(self.fp64_slices_kinv or self.fp64_slices, self.fp64_slices)
+            self._cfg = (ops.gemm_cfg(self._oz, ops.GEMM_INT8_DIGITS, self.fp64_slices, md),
+                         ops.gemm_cfg(self._oz, ops.GEMM_INT8_DIGITS, sk, md))
+
+    @property
+    def cfg_main(self):
+        return self._cfg[0]
+
+    @property
+    def cfg_kinv(self):
+        return self._cfg[1]
 
     def release(self):
-        """Drop the HBM workspaces (and un-configure the INT8 path if it points at this engine's scratch)."""
+        """Drop the HBM workspaces and the plane scratch."""
         self._ws, self._ws_key = None, None
-        if self._oz is not None:
-            if ops._fp64_ws_ref is self._oz:
-                ops.set_fp64_emulation(None, 0, self.fp64_min_dim)
-            self._oz = None
-
-    def __del__(self):
-        try:
-            self.release()
-        except Exception:   # interpreter shutdown: the library or torch may already be gone
-            pass
+        self._oz, self._cfg, self._cfg_key = None, (None, None), None
 
     def xmean(self, X: torch.Tensor) -> torch.Tensor:
         key = (X.data_ptr(), X._version, tuple(X.shape), str(X.device))
@@ -109,44 +152,78 @@ class LatentEngine:
         return self._xmean
 
     # -- factorisation with gpytorch's psd_safe_cholesky retry semantics ---------
-    def _gram_potrf(self, ws, Z, zn, kid, os_, noise, n, max_tries):
+    # The first attempt is launched WITHOUT a host synchronisation: `info` (first bad pivot per latent, like
+    # cholesky_ex) and a finite-inputs flag are copied to pinned memory behind the factorisation and an event is
+    # recorded.  The caller queues everything that follows (solves, inverse, sweep) and only then waits for that
+    # event, so the GPU queue never drains; the jitter retry -- the rare path -- re-runs synchronously.
+    def _gram_potrf_launch(self, ws, Z, zn, kid, os_, noise, n):
         q = Z.shape[0]
         K, dinv, info = ws["K"], ws["dinv"], ws["info"]
-        jitter = torch.zeros(q, dtype=torch.float64, device=Z.device)
         # psd_safe_cholesky refuses a matrix with NaN entries before it factors anything.  Every entry of K is a
         # function of zn, Z, the outputscale and the noise, so the O(qn) inputs are checked instead of the n^2
         # matrix (the integer tensor path would turn a NaN into an arbitrary finite number, not propagate it).
         finite = torch.isfinite(zn).all() & torch.isfinite(noise).all()
         if os_ is not None:
             finite = finite & torch.isfinite(os_).all()
-        if not bool(finite):
-            raise NanError("cholesky: the kernel matrix contains NaN (non-finite inputs, lengthscales, outputscale "
-                           "or noise)")
+        self.generation += 1
         ops.gram(Z, zn, kid, os_, noise, K, n)
         self._mark("gram")
-        ops.potrf(K, dinv, info)
+        ops.potrf(K, dinv, info[:q], self.cfg_main)
+        info[q:] = (~finite).to(torch.int32)
+        if self._pinned is None or self._pinned.numel() != q + 1:
+            self._pinned = torch.empty((q + 1,), dtype=torch.int32).pin_memory()
+        self._pinned.copy_(info, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
         self._mark("potrf")
-        bad = info.cpu()
+        return ev
+
+    def _gram_potrf_resolve(self, ev, ws, Z, zn, kid, os_, noise, n, max_tries):
+        """Wait for the factorisation's status; returns True if a jitter retry re-factorised K (everything
+        queued after the first attempt must then be redone)."""
+        q = Z.shape[0]
+        K, dinv, info = ws["K"], ws["dinv"], ws["info"]
+        ev.synchronize()
+        host = self._pinned.clone()
+        if int(host[q]) != 0:
+            raise NanError("cholesky: the kernel matrix contains NaN (non-finite inputs, lengthscales, outputscale "
+                           "or noise)")
+        bad = host[:q]
         if not bool(bad.any()):
             self.last_jitter = None
-            return
+            return False
+        jitter = torch.zeros(q, dtype=torch.float64, device=Z.device)
         base = settings.cholesky_jitter.value()
         prev_bad = bad
         new = 0.0
+        # a failed member left garbage in its K; the others may have been overwritten by work queued after
+        # the factorisation (the inverse runs in place), so every member is rebuilt, jitter only where needed
+        first = True
         for i in range(max_tries):
             new = base * (10**i)
             warnings.warn(f"A not p.d., added jitter of {new:.1e} to the diagonal", RuntimeWarning)
-            for l in torch.nonzero(prev_bad).flatten().tolist():
-                jitter[l] = new
+            members = range(q) if first else torch.nonzero(prev_bad).flatten().tolist()
+            failing = set(torch.nonzero(prev_bad).flatten().tolist())
+            self.generation += 1
+            for l in members:
+                if l in failing:
+                    jitter[l] = new
                 sl = slice(l, l + 1)
                 da = (noise[sl] + jitter[sl]).contiguous()
                 ops.gram(Z[sl], zn[sl], kid, None if os_ is None else os_[sl], da, K[sl], n)
-                ops.potrf(K[sl], dinv[sl], info[sl])
-            prev_bad = info.cpu()
+                ops.potrf(K[sl], dinv[sl], info[sl], self.cfg_main)
+            first = False
+            now = info[:q].cpu()
+            # members that were fine stay fine (same matrix); only previously failing ones can still fail
+            prev_bad = now
             if not bool(prev_bad.any()):
                 self.last_jitter = jitter
-                return
+                return True
         raise NotPSDError(f"Matrix not positive definite after repeatedly adding jitter up to {new:.1e}.")
+
+    def _gram_potrf(self, ws, Z, zn, kid, os_, noise, n, max_tries):
+        ev = self._gram_potrf_launch(ws, Z, zn, kid, os_, noise, n)
+        self._gram_potrf_resolve(ev, ws, Z, zn, kid, os_, noise, n, max_tries)
 
     # -- training: log-probabilities and all partial gradients -------------------
     def log_prob_and_grads(self, X, TY, ell, os_, noise, kid, need_grad, max_tries=None):
@@ -161,34 +238,32 @@ class LatentEngine:
         mark = self._mark
         mark("start")
         Z, zn = ops.scale_inputs(X, self.xmean(X), ell, np_)
-        self._gram_potrf(ws, Z, zn, kid, os_, noise, n, max_tries)
-        mark("retry")
+        ev = self._gram_potrf_launch(ws, Z, zn, kid, os_, noise, n)
         K, dinv = ws["K"], ws["dinv"]
-        if not need_grad:
+
+        def rest():
+            # z, alpha, the quadratic form and the log-determinant come from L itself (two HBM-bound block
+            # substitutions, csrc/trsv.cu) at full FP64-grade accuracy.  The explicit inverse K^-1 = L^-T L^-1
+            # (trtri + lauum, 2/3 of the flops of the iteration) then feeds ONLY the gradient sweep
+            # tr((alpha alpha^T - K^-1) dK), so both steps may run at the reduced cfg_kinv precision.
             z, alpha, quad, logdet = ops.solve_logdet(K, dinv, TY, n, ws["rhs"])
+            lp = -0.5 * (quad + logdet + n * math.log(2 * math.pi))
             mark("solve_logdet")
-            return -0.5 * (quad + logdet + n * math.log(2 * math.pi)), None
-        # training step.  z, alpha, the quadratic form and the log-determinant come from L itself (two HBM-bound
-        # block substitutions, csrc/trsv.cu) at full FP64-grade accuracy.  The explicit inverse K^-1 = L^-T L^-1
-        # (trtri + lauum, 2/3 of the flops of the iteration) then feeds ONLY the gradient sweep
-        # tr((alpha alpha^T - K^-1) dK), so both steps may run with fp64_slices_kinv planes.
-        z, alpha, quad, logdet = ops.solve_logdet(K, dinv, TY, n, ws["rhs"])
-        lp = -0.5 * (quad + logdet + n * math.log(2 * math.pi))
-        mark("solve_logdet")
-        s_kinv = min(self.fp64_slices_kinv, self.fp64_slices)
-        lower = self._oz is not None and 0 < s_kinv < self.fp64_slices and np_ >= 2 * self.fp64_min_dim
-        if lower:
-            ops.set_fp64_emulation(self._oz, s_kinv, self.fp64_min_dim)
-        try:
-            ops.trtri(K, dinv)
-            ops.lauum(K)
-        finally:
-            if lower:
-                ops.set_fp64_emulation(self._oz, self.fp64_slices, self.fp64_min_dim)
-        mark("potri")
-        g_ell, g_os, g_noise = ops.grad_sweep(K, alpha, Z, zn, ell, kid, os_, n)
-        mark("grad_sweep")
-        return lp, (-alpha, g_ell, (g_os if os_ is not None else None), g_noise)
+            if not need_grad:
+                return lp, None
+            self.generation += 1
+            ops.trtri(K, dinv, self.cfg_kinv)
+            ops.lauum(K, self.cfg_kinv)
+            mark("potri")
+            g_ell, g_os, g_noise = ops.grad_sweep(K, alpha, Z, zn, ell, kid, os_, n)
+            mark("grad_sweep")
+            return lp, (-alpha, g_ell, (g_os if os_ is not None else None), g_noise)
+
+        out = rest()                      # queued behind the factorisation before its status is known
+        if self._gram_potrf_resolve(ev, ws, Z, zn, kid, os_, noise, n, max_tries):
+            mark("retry")
+            out = rest()                  # a jitter retry re-factorised K: redo what depended on it
+        return out
 
     # -- optional phase timing (CUDA events on the launch stream; used by bench.py) --
     profile = None
@@ -216,6 +291,7 @@ class LatentEngine:
         ws = self.workspace(X.device, q, n)
         np_ = ws["K"].shape[1]
         Z, zn = ops.scale_inputs(X, self.xmean(X), ell, np_)
+        self.generation += 1
         ops.gram(Z, zn, kid, os_, noise, ws["K"], n)
         K = ws["K"][:, :n, :n]
         return torch.tril(K) + torch.tril(K, -1).transpose(1, 2)
@@ -232,7 +308,8 @@ class LatentEngine:
         self._gram_potrf(ws, Z, zn, kid, os_, noise, n, max_tries)
         K, dinv = ws["K"], ws["dinv"]
         _, alpha, _, _ = ops.solve_logdet(K, dinv, TY, n, ws["rhs"])
-        ops.potri(K, dinv)
+        self.generation += 1
+        ops.potri(K, dinv, self.cfg_main)
         sigma2 = 1.0 / torch.diagonal(K, dim1=1, dim2=2)[:, :n]
         return sigma2, alpha * sigma2
 
@@ -250,7 +327,13 @@ class LatentEngine:
         self._gram_potrf(ws, Z, zn, kid, os_, noise, n, max_tries)
         _, alpha, _, _ = ops.solve_logdet(ws["K"], ws["dinv"], TY, n, ws["rhs"])
         return dict(L=ws["K"], dinv=ws["dinv"], alpha=alpha, Z=Z, zn=zn, xmean=xmean, ell=ell, os=os_, kid=kid, n=n,
-                    d=d, q=q)
+                    d=d, q=q, generation=self.generation)
+
+    def state_is_current(self, st) -> bool:
+        """False once anything (training step, compute_loo, kernel_cond, another factorize) has rewritten the
+        shared workspace the prediction state points into."""
+        return st is not None and st.get("generation") == self.generation and self._ws is not None and \
+            st["L"].data_ptr() == self._ws["K"].data_ptr()
 
     @staticmethod
     def tile_points(q: int, np_: int, budget_bytes: int = 6 << 30) -> int:
@@ -263,6 +346,8 @@ class LatentEngine:
         np_ = st["L"].shape[1]
         ns = Xs.shape[0]
         dev = Xs.device
+        if not self.state_is_current(st):
+            raise RuntimeError("stale prediction state: the engine workspace was rewritten after factorize()")
         self._configure_fp64(dev, np_, q)
         mt_full = tile or self.tile_points(q, np_)
         lat_mean = torch.empty((q, ns), dtype=torch.float64, device=dev)
@@ -278,6 +363,6 @@ class LatentEngine:
             ops.cross_gram(st["Z"], st["zn"], Zt, znt, st["kid"], st["os"], Kx, n, mt)
             lat_mean[:, s0:s0 + cnt] = ops.latent_mean(Kx, st["alpha"], n, mt)[:, :cnt]
             if need_var:
-                ops.trsm(2, st["L"], st["dinv"], Kx, 1.0)
+                ops.trsm(2, st["L"], st["dinv"], Kx, 1.0, self.cfg_main)
                 lat_var[:, s0:s0 + cnt] = ops.latent_var(Kx, st["os"], mt)[:, :cnt]
         return lat_mean, lat_var

@@ -55,10 +55,18 @@ class ProjectedLMCmll(gp.mlls.ExactMarginalLogLikelihood):
         self._S_key = None
 
     def _second_moment(self, target: torch.Tensor) -> torch.Tensor:
-        key = (target.data_ptr(), target._version, tuple(target.shape))
+        """S = Y^T Y.  Cached only for the model's own ``train_y`` buffer (object identity + version counter);
+        any other target tensor is reduced afresh on every call -- a recycled allocation of a different tensor
+        can share data_ptr, shape and version with a freed one, so those do not identify it."""
+        def second_moment(t):
+            Y = t.detach().to(torch.float64).contiguous()
+            return ops.project_bwd(Y, Y.T.contiguous())        # S[t, t'] = sum_i Y[i,t] Y[i,t']
+
+        if target is not self.model.train_y:
+            return second_moment(target)
+        key = (target._version, target.data_ptr(), tuple(target.shape), str(target.device))
         if self._S_key != key:
-            Y = target.detach().to(torch.float64).contiguous()
-            self._S = ops.project_bwd(Y, Y.T.contiguous())      # S[t, t'] = sum_i Y[i,t] Y[i,t']
+            self._S = second_moment(target)
             self._S_key = key
         return self._S
 

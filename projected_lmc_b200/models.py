@@ -315,7 +315,9 @@ class ProjectedGPModel(ExactGPModel):
 
     def _prediction_state(self):
         key = tuple((id(p), p._version) for p in self.parameters()) + (self.train_y._version, self._latent_range)
-        if self._pred_cache is None or self._pred_key != key:
+        # the factor lives in the engine's shared workspace: compute_loo / kernel_cond / a training-mode handle
+        # rewrite it, so the cache is also checked against the engine's workspace generation
+        if self._pred_cache is None or self._pred_key != key or not self._engine.state_is_current(self._pred_cache):
             with torch.no_grad():
                 X = _as_f64(self.train_inputs[0])
                 kid, ell, os_, noise = self._kernel_params()
@@ -394,8 +396,9 @@ class ProjectedGPModel(ExactGPModel):
             ops.mix_tasks(lat_mean, lat_var, Ht, var_add, mean, var, ns)
             if self._dist_group is not None:
                 import torch.distributed as dist
-                dist.all_reduce(mean, group=self._dist_group)
-                dist.all_reduce(var, group=self._dist_group)
+                both = torch.stack((mean, var))          # one collective for the two [n*, p] tiles
+                dist.all_reduce(both, group=self._dist_group)
+                mean, var = both[0], both[1]
             if has_bad:
                 mean[bad_rows] = float("nan")
                 var[bad_rows] = float("nan")

@@ -1,14 +1,18 @@
 """Thin torch-tensor wrappers over the C ABI (one Python function per entry point).
 
-Every wrapper takes CUDA float64 tensors, launches on the current stream and
-returns immediately (no synchronisation).  Shapes follow include/plmc_b200.h.
+Every wrapper takes CUDA float64 tensors, launches on the current stream of the device that owns
+them and returns immediately (no synchronisation).  Shapes follow include/plmc_b200.h.
 """
 from __future__ import annotations
+
+import ctypes
+import functools
 
 import torch
 
 from . import _cabi
-from ._cabi import check, lib, npad, ptr, stream
+from ._cabi import (GEMM_FLAG_SINGLE_CTA, GEMM_FP64, GEMM_INT8_DIGITS, GEMM_INT8_RNS, GemmCfg, PlmcError, check, lib,
+                    npad, ptr, stream)
 
 KERNEL_IDS = {"rbf": 0, "matern52": 1, "matern32": 2, "matern12": 3}
 
@@ -16,10 +20,48 @@ KERNEL_IDS = {"rbf": 0, "matern52": 1, "matern32": 2, "matern12": 3}
 A_KC_B_KC, A_KC_B_NC, A_MC_B_KC, A_MC_B_NC = 0, 1, 2, 3
 
 
+def _on_device(fn):
+    """Run the wrapped call with the device of its tensor arguments current (the library launches on the
+    current device and its current stream); tensors on different devices are an error."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = None
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if not a.is_cuda:
+                    raise PlmcError("libplmc_b200 was handed a non-CUDA tensor; there is no CPU fallback")
+                if dev is None:
+                    dev = a.device
+                elif a.device != dev:
+                    raise PlmcError(f"libplmc_b200 call with tensors on different devices: {dev} and {a.device}")
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
+def gemm_cfg(ws, mode: int, precision: int, min_dim: int = 512, flags: int = 0):
+    """plmc_gemm_cfg for the factorisation calls (None = pure FP64).  The struct keeps its scratch tensor alive."""
+    if ws is None or mode == GEMM_FP64 or precision <= 0:
+        return None
+    cfg = GemmCfg(ptr(ws), ws.numel() * ws.element_size(), int(mode), int(precision), max(128, int(min_dim)),
+                  int(flags))
+    cfg._keepalive = ws
+    return cfg
+
+
+def _cfgp(cfg):
+    return None if cfg is None else ctypes.byref(cfg)
+
+
 def _bstride(t: torch.Tensor) -> int:
     return t.stride(0) if t.dim() == 3 else 0
 
 
+@_on_device
 def gemm(layout, A, B, C, M, N, K, alpha=1.0, beta=0.0, lower=False, triA=False, triB=False):
     """C[b] = alpha * op(A[b]) op(B[b]) + beta * C[b]; A, B, C are [batch, rows, ld] views."""
     batch = C.shape[0]
@@ -37,25 +79,29 @@ def alloc_dinv(np_: int, batch: int, device) -> torch.Tensor:
     return torch.empty((batch, np_ // 128, 128, 128), dtype=torch.float64, device=device)
 
 
-def potrf(K: torch.Tensor, dinv: torch.Tensor, info: torch.Tensor):
+@_on_device
+def potrf(K: torch.Tensor, dinv: torch.Tensor, info: torch.Tensor, cfg=None):
     """In-place lower Cholesky of K [batch, npad, ld]; info int32 [batch]."""
     b, np_, _ = K.shape
-    check(lib().plmc_potrf_batched(ptr(K), K.stride(1), K.stride(0), np_, b, ptr(dinv), ptr(info), stream()), "potrf")
+    check(lib().plmc_potrf_batched(ptr(K), K.stride(1), K.stride(0), np_, b, ptr(dinv), ptr(info), _cfgp(cfg),
+                                   stream()), "potrf")
 
 
-def trsm(op: int, L, dinv, B, alpha=1.0):
+@_on_device
+def trsm(op: int, L, dinv, B, alpha=1.0, cfg=None):
     """op 0: X L^T = aB | 1: X L = aB (B [batch, m, npad]) | 2: L X = aB | 3: L^T X = aB (B [batch, npad, m])."""
     b, np_, _ = L.shape
     m = B.shape[1] if op in (0, 1) else B.shape[2]
     check(
         lib().plmc_trsm_batched(
             op, ptr(L), L.stride(1), L.stride(0), np_, b, ptr(dinv), ptr(B), B.stride(1), B.stride(0), m,
-            float(alpha), stream(),
+            float(alpha), _cfgp(cfg), stream(),
         ),
         "trsm",
     )
 
 
+@_on_device
 def solve_logdet(L, dinv, y, n, rhs=None):
     """z = L^-1 y, alpha = L^-T z, |z|^2, 2 sum log L_ii for y [batch, >=n]."""
     b, np_, _ = L.shape
@@ -76,41 +122,25 @@ def solve_logdet(L, dinv, y, n, rhs=None):
     return z, alpha, quad, logdet
 
 
-def trmv_solve_logdet(Linv, y, n, ws=None):
-    """Same outputs as solve_logdet, from the explicit inverse factor Linv [batch, npad, ld]."""
-    b, np_, _ = Linv.shape
-    dev = Linv.device
-    if ws is None:
-        ws = torch.empty((b, 128, np_), dtype=torch.float64, device=dev)
-    z = torch.empty((b, n), dtype=torch.float64, device=dev)
-    alpha = torch.empty((b, n), dtype=torch.float64, device=dev)
-    quad = torch.empty((b,), dtype=torch.float64, device=dev)
-    logdet = torch.empty((b,), dtype=torch.float64, device=dev)
-    check(
-        lib().plmc_trmv_solve_logdet(
-            ptr(Linv), Linv.stride(1), Linv.stride(0), n, np_, b, ptr(y), y.stride(0), ptr(ws), ptr(z), ptr(alpha), n,
-            ptr(quad), ptr(logdet), stream(),
-        ),
-        "trmv_solve_logdet",
-    )
-    return z, alpha, quad, logdet
-
-
-def trtri(L, dinv):
+@_on_device
+def trtri(L, dinv, cfg=None):
     b, np_, _ = L.shape
-    check(lib().plmc_trtri_batched(ptr(L), L.stride(1), L.stride(0), np_, b, ptr(dinv), stream()), "trtri")
+    check(lib().plmc_trtri_batched(ptr(L), L.stride(1), L.stride(0), np_, b, ptr(dinv), _cfgp(cfg), stream()), "trtri")
 
 
-def lauum(L):
+@_on_device
+def lauum(L, cfg=None):
     b, np_, _ = L.shape
-    check(lib().plmc_lauum_batched(ptr(L), L.stride(1), L.stride(0), np_, b, stream()), "lauum")
+    check(lib().plmc_lauum_batched(ptr(L), L.stride(1), L.stride(0), np_, b, _cfgp(cfg), stream()), "lauum")
 
 
-def potri(L, dinv):
+@_on_device
+def potri(L, dinv, cfg=None):
     b, np_, _ = L.shape
-    check(lib().plmc_potri_batched(ptr(L), L.stride(1), L.stride(0), np_, b, ptr(dinv), stream()), "potri")
+    check(lib().plmc_potri_batched(ptr(L), L.stride(1), L.stride(0), np_, b, ptr(dinv), _cfgp(cfg), stream()), "potri")
 
 
+@_on_device
 def project_fwd(Y: torch.Tensor, T: torch.Tensor) -> torch.Tensor:
     n, p = Y.shape
     q = T.shape[1]
@@ -119,6 +149,7 @@ def project_fwd(Y: torch.Tensor, T: torch.Tensor) -> torch.Tensor:
     return TY
 
 
+@_on_device
 def project_bwd(Y: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
     n, p = Y.shape
     q = G.shape[0]
@@ -132,6 +163,7 @@ def dpad_of(d: int) -> int:
     return ((d + 3) // 4) * 4
 
 
+@_on_device
 def col_mean(X: torch.Tensor) -> torch.Tensor:
     n, d = X.shape
     out = torch.empty((d,), dtype=torch.float64, device=X.device)
@@ -139,6 +171,7 @@ def col_mean(X: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@_on_device
 def scale_inputs(X, xmean, ell, rows_pad):
     """Z [q, rows_pad, dpad], zn [q, rows_pad]."""
     n, d = X.shape
@@ -151,6 +184,7 @@ def scale_inputs(X, xmean, ell, rows_pad):
     return Z, zn
 
 
+@_on_device
 def gram(Z, zn, kernel_id, os_, diag_add, K, n):
     q, np_, dp = Z.shape
     check(
@@ -160,6 +194,7 @@ def gram(Z, zn, kernel_id, os_, diag_add, K, n):
     )
 
 
+@_on_device
 def cross_gram(Ztr, zntr, Zte, znte, kernel_id, os_, Kx, n, mt):
     q, np_, dp = Ztr.shape
     check(
@@ -169,6 +204,7 @@ def cross_gram(Ztr, zntr, Zte, znte, kernel_id, os_, Kx, n, mt):
     )
 
 
+@_on_device
 def grad_sweep(Kinv, alpha, Z, zn, ell, kernel_id, os_, n):
     q, np_, dp = Z.shape
     d = ell.shape[1]
@@ -186,6 +222,7 @@ def grad_sweep(Kinv, alpha, Z, zn, ell, kernel_id, os_, n):
     return g_ell, g_os, g_noise
 
 
+@_on_device
 def latent_mean(Kx, alpha, n, mt):
     q = Kx.shape[0]
     out = torch.empty((q, mt), dtype=torch.float64, device=Kx.device)
@@ -194,6 +231,7 @@ def latent_mean(Kx, alpha, n, mt):
     return out
 
 
+@_on_device
 def latent_var(V, os_, mt):
     q, np_, _ = V.shape
     out = torch.empty((q, mt), dtype=torch.float64, device=V.device)
@@ -202,26 +240,38 @@ def latent_var(V, os_, mt):
     return out
 
 
+@_on_device
 def mix_tasks(lat_mean, lat_var, H, var_add, mean, var, mt, accumulate=False):
     q, p = H.shape
     check(lib().plmc_mix_tasks(ptr(lat_mean), ptr(lat_var), lat_mean.stride(0), ptr(H), ptr(var_add), ptr(mean),
                                ptr(var), mt, p, q, int(accumulate), stream()), "mix_tasks")
 
 
+@_on_device
 def peak_dmma(blocks, threads, iters, scratch):
     check(lib().plmc_peak_dmma(blocks, threads, iters, ptr(scratch), stream()), "peak_dmma")
     return blocks * (threads // 32) * iters * 16 * 512
 
 
+@_on_device
 def peak_dfma(blocks, threads, iters, scratch):
     check(lib().plmc_peak_dfma(blocks, threads, iters, ptr(scratch), stream()), "peak_dfma")
     return blocks * threads * iters * 16 * 2
 
 
+@_on_device
 def peak_copy(src, dst):
     n = src.numel()
     check(lib().plmc_peak_copy(ptr(src), ptr(dst), n, stream()), "peak_copy")
     return 16 * n
+
+
+@_on_device
+def peak_i8(iters, scratch, cta_group=2):
+    """Shared-memory-resident tcgen05.mma.kind::i8 loop on every SM: returns the INT8 operations issued."""
+    ops_ = ctypes.c_double(0.0)
+    check(lib().plmc_peak_i8(int(iters), int(cta_group), ptr(scratch), ctypes.byref(ops_), stream()), "peak_i8")
+    return ops_.value
 
 
 def stats_reset():
@@ -239,15 +289,14 @@ def trace_report():
 
 def stats_get():
     """(kernel launches, GEMM launches, GEMM algorithmic FLOPs) since the last reset."""
-    import ctypes
-
     a, b, c = ctypes.c_longlong(0), ctypes.c_longlong(0), ctypes.c_double(0.0)
     check(_cabi.load().plmc_stats_get(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "stats_get")
     return a.value, b.value, c.value
 
 
+@_on_device
 def ozaki_gemm(layout, A, B, C, M, N, K, alpha=1.0, beta=0.0, lower=False, slices=7, same_operand=False, ws=None):
-    """C = alpha op(A) op(B) + beta C (2-D views) on the tcgen05 INT8 path (FP64 via 8-bit planes)."""
+    """C = alpha op(A) op(B) + beta C (2-D views) on the tcgen05 INT8 path (FP64 via 8-bit digit planes)."""
     need = lib().plmc_ozaki_ws_bytes(M, N, K, slices, int(same_operand))
     if ws is None or ws.numel() < need:
         ws = torch.empty((need,), dtype=torch.uint8, device=C.device)
@@ -260,18 +309,21 @@ def ozaki_gemm(layout, A, B, C, M, N, K, alpha=1.0, beta=0.0, lower=False, slice
     return C
 
 
-_fp64_ws_ref = None   # keeps the scratch the library currently points at alive (the setting is process-wide)
+def rns_bits(moduli: int, K: int) -> int:
+    return int(_cabi.load().plmc_rns_bits(int(moduli), int(K)))
 
 
-def set_fp64_emulation(ws, slices: int, min_dim: int = 1024):
-    """Route the large GEMMs of potrf/trsm/trtri/lauum through the tcgen05 INT8 path (slices=0: off).
-
-    The library stores the raw scratch pointer; this wrapper holds a reference to the tensor for as long as it
-    is the configured one, so an engine that goes away cannot leave the library writing into freed memory."""
-    global _fp64_ws_ref
-    if ws is None or slices == 0:
-        check(lib().plmc_set_fp64_emulation(None, 0, 0, max(128, min_dim)), "set_fp64_emulation")
-        _fp64_ws_ref = None
-    else:
-        check(lib().plmc_set_fp64_emulation(ptr(ws), ws.numel(), slices, max(128, min_dim)), "set_fp64_emulation")
-        _fp64_ws_ref = ws
+@_on_device
+def rns_gemm(layout, A, B, C, M, N, K, alpha=1.0, beta=0.0, lower=False, moduli=16, same_operand=False, ws=None,
+             flags=0):
+    """C = alpha op(A) op(B) + beta C (2-D views) on the tcgen05 INT8 path, residue-number-system scheme."""
+    if ws is None:
+        need = lib().plmc_rns_ws_bytes(M, N, K, moduli, int(same_operand), int(lower))
+        ws = torch.empty((need,), dtype=torch.uint8, device=C.device)
+    check(
+        lib().plmc_rns_gemm(layout, ptr(A), A.stride(-2), ptr(B), B.stride(-2), ptr(C), C.stride(-2), M, N, K,
+                            float(alpha), float(beta), int(lower), int(moduli), int(same_operand), ptr(ws), ws.numel(),
+                            int(flags), stream()),
+        "rns_gemm",
+    )
+    return C

@@ -45,6 +45,9 @@ def test_sass_has_fp64_tensor_core_and_async_copy_instructions():
     sass = subprocess.run(["cuobjdump", "-sass", str(_cabi.lib_path())], capture_output=True, text=True).stdout
     assert "DMMA.8x8x4" in sass, "FP64 tensor-core MMA missing from the sm_100a build"
     assert "LDGSTS" in sass, "cp.async staging missing"
+    # the dominant kernels: tcgen05 INT8 MMA (single CTA and CTA pair), TMEM loads, bulk async copies
+    for mnemonic in ("UTCIMMA", "UTCIMMA.2CTA", "LDTM", "UBLKCP", "UTCBAR", "IDP.4A"):
+        assert mnemonic in sass, f"{mnemonic} missing from the sm_100a build"
     assert "sm_100a" in sass or "SM100" in sass.upper()
 
 

@@ -119,12 +119,12 @@ def test_accuracy_scales_with_slices(slices, tol):
     assert rel_err(C, ref) < tol
 
 
-@pytest.fixture
-def force_emulation_everywhere():
-    old = LatentEngine.fp64_slices, LatentEngine.fp64_min_dim
-    LatentEngine.fp64_slices, LatentEngine.fp64_min_dim = 7, 128
+@pytest.fixture(params=["digits", "rns"])
+def force_emulation_everywhere(request):
+    old = LatentEngine.fp64_slices, LatentEngine.fp64_min_dim, LatentEngine.gemm_mode
+    LatentEngine.fp64_slices, LatentEngine.fp64_min_dim, LatentEngine.gemm_mode = 7, 128, request.param
     yield
-    LatentEngine.fp64_slices, LatentEngine.fp64_min_dim = old
+    LatentEngine.fp64_slices, LatentEngine.fp64_min_dim, LatentEngine.gemm_mode = old
 
 
 @pytest.mark.parametrize("variant,kernel", [("PLMC", "matern52"), ("PLMC_fast", "rbf")])
@@ -150,20 +150,21 @@ def test_model_path_with_every_gemm_emulated_matches_oracle(force_emulation_ever
 
 
 def test_emulated_and_dmma_paths_agree_at_n_6000():
-    """Beyond the oracle's reach: same model, both arithmetic paths (default thresholds)."""
+    """Beyond the oracle's reach: same model, all three arithmetic paths (default thresholds)."""
     X, Y, _, _ = synth(6000, 8, 6, 2, seed=11)
     out = {}
-    old = LatentEngine.fp64_slices
+    old = LatentEngine.gemm_mode
     try:
-        for mode in (0, 7):
-            LatentEngine.fp64_slices = mode
+        for mode in ("fp64", "digits", "rns"):
+            LatentEngine.gemm_mode = mode
             m = make_model(X, Y, 2, variant="PLMC", kernel="matern52").cuda()
             loss = -ProjectedLMCmll(m.likelihood, m)(m(X.cuda()), Y.cuda())
             loss.backward()
             out[mode] = (loss.item(), {k: p.grad.clone() for k, p in m.named_parameters()})
             del m
     finally:
-        LatentEngine.fp64_slices = old
-    assert abs(out[0][0] - out[7][0]) <= 1e-10 * abs(out[0][0])
-    for k in out[0][1]:
-        assert rel_err(out[7][1][k], out[0][1][k]) <= 1e-7, k
+        LatentEngine.gemm_mode = old
+    for mode in ("digits", "rns"):
+        assert abs(out["fp64"][0] - out[mode][0]) <= 1e-10 * abs(out["fp64"][0]), mode
+        for k in out["fp64"][1]:
+            assert rel_err(out[mode][1][k], out["fp64"][1][k]) <= 1e-7, (mode, k)
