@@ -1,16 +1,18 @@
 #!/usr/bin/env python
-"""Benchmark of the projected-LMC hot path (contract: see the repo brief / DESIGN.md).
+"""Benchmark of the projected-LMC hot path (contract: see the repo brief / DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5]
+                    [--scaling weak|strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): synthetic SARCOS-shaped projected LMC,
-n = 44,484 points, d = 21, Matern-5/2 ARD, fp64, PLMC variant; 4 latents and 7 tasks
-PER GPU (weak scaling: at N GPUs the model has 4N latents / 7N tasks, each rank owns 4
-latents, one NCCL all-reduce of the loss + gradients per step).  One step = one training
-iteration of the reference's loop (experiments.py:263-273): zero_grad, MLL forward, full backward to
-every raw parameter, AdamW step, learning-rate scheduler step.  `value` counts
-4-latent SARCOS-shaped model iterations per second (N per step at N GPUs).
+Default workload (BASELINE.json configs[1], "C2"): synthetic SARCOS-shaped projected LMC, n = 44,484 points, d = 21,
+Matern-5/2 ARD, fp64, PLMC variant; 4 latents and 7 tasks PER GPU (weak scaling: at N GPUs the model has 4N latents /
+7N tasks, each rank owns 4 latents, one NCCL all-reduce of the loss + gradients per step).  One step = one training
+iteration of the reference's loop (experiments.py:263-273): zero_grad, MLL forward, full backward to every raw
+parameter, AdamW step, learning-rate scheduler step.  `value` counts 4-latent SARCOS-shaped model iterations per
+second (N per step at N GPUs).  --scaling strong keeps the NAMED model fixed and splits its latents over the ranks
+(C2: 4 latents -> at most 4 GPUs; C4: 32 latents; C5: 8 latents).  c3 is the prediction config (metric: predictive
+mean/variance points per second; test points are sharded over the ranks, every rank holds all factors).
 """
 from __future__ import annotations
 
@@ -31,30 +33,47 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+# per-GPU share (p, q), and the totals / GPU count the BASELINE.json config is quoted on
 WORKLOADS = {
-    # name: (n, d, tasks/gpu, latents/gpu, kernel, variant)
-    "c2": dict(n=44484, d=21, p=7, q=4, kernel="matern52", label="C2 SARCOS-shaped projected LMC"),
-    "c1": dict(n=1000, d=6, p=50, q=10, kernel="rbf", label="C1 experiments.py-style projected LMC"),
-    # C4 / C5 are quoted on 8 GPUs (500 tasks / 32 latents, 20 tasks / 8 latents): per-GPU shares below
-    "c4": dict(n=20000, d=8, p=63, q=4, kernel="rbf", label="C4 many-task projected LMC (4 latents, 63 tasks per GPU)"),
-    "c5": dict(n=100000, d=4, p=3, q=1, kernel="rbf", label="C5 large-n projected LMC (1 latent, 3 tasks per GPU)"),
+    "c1": dict(n=1000, d=6, p=50, q=10, kernel="rbf", named_gpus=1, named_p=50, named_q=10, steps=50,
+               label="C1 experiments.py-style projected LMC"),
+    "c2": dict(n=44484, d=21, p=7, q=4, kernel="matern52", named_gpus=1, named_p=7, named_q=4, steps=3,
+               label="C2 SARCOS-shaped projected LMC"),
+    "c3": dict(n=20000, d=8, p=100, q=16, kernel="rbf", named_gpus=8, named_p=100, named_q=16, steps=1,
+               n_test=1000000, label="C3 batched predictive mean/variance"),
+    "c4": dict(n=20000, d=8, p=63, q=4, kernel="rbf", named_gpus=8, named_p=500, named_q=32, steps=3,
+               label="C4 many-task projected LMC"),
+    "c5": dict(n=100000, d=4, p=3, q=1, kernel="rbf", named_gpus=8, named_p=20, named_q=8, steps=2,
+               label="C5 large-n projected LMC"),
 }
-CPU_SAMPLE_N = 2000
+CPU_FIT_NS = (1000, 2000, 4000)          # in-line cpu_baseline of the default run (~10 s of host work)
+REFERENCE_FIT_NS = (2000, 4000, 8000)    # --impl reference (~1-2 min of host work)
+LIBRARY_N = 8192                         # torch -> cuSOLVER restatement on the same GPU
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (default: per workload)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--points", dest="n", type=int, default=0, help="override n (debug only; reported in config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-predict", action="store_true")
-    ap.add_argument("--test-points", type=int, default=8192)
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--test-points", type=int, default=0)
     return ap.parse_args()
+
+
+def model_shape(cfg, world, scaling):
+    """(p_total, q_total) of the model run on `world` GPUs."""
+    if scaling == "strong" or world == cfg["named_gpus"]:
+        return cfg["named_p"], cfg["named_q"]
+    return cfg["p"] * world, cfg["q"] * world
 
 
 def make_data(n, d, p, q, seed=0):
@@ -112,7 +131,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         lines = [(ts, ln) for ts, ln in self.lines if t0 is None or (t0 <= ts <= t1)]
         window = "timed region"
@@ -127,12 +146,14 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
+                pw.append(float(f[3]))
             except ValueError:
                 continue
             for nm, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_median": statistics.median(pw) if pw else None,
                 "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
@@ -160,46 +181,76 @@ def dmma_peak_tflops():
     return best
 
 
-def roofline_entry(eng, achieved, dmma_peak, peaks, peak_src, gemm_flops, gemm_launches, fact_ms, steps):
+def i8_peak_tops():
+    """Live INT8 tensor-pipe peak: shared-memory-resident tcgen05.mma.kind::i8 loop on every SM (plmc_peak_i8)."""
+    from projected_lmc_b200 import ops
+
+    scratch = torch.zeros(16, dtype=torch.float64, device="cuda")
+    best = 0.0
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n_ops = ops.peak_i8(20000, scratch, 2)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, n_ops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+def products_per_fp64_product(eng):
+    """INT8 products per FP64 product, flop-weighted over one training iteration: the factorisation (1/3 of the
+    q n^3 FLOP) runs at the main precision, the explicit inverse (2/3; K^-1 feeds only the gradients) at the
+    reduced one.  (main, inverse, weighted, description)"""
+    mode = eng.emulation_mode() if hasattr(eng, "emulation_mode") else ("digits" if getattr(eng, "fp64_slices", 0) else "fp64")
+    if mode == "rns":
+        m = eng.rns_moduli
+        mk = min(getattr(eng, "rns_moduli_kinv", 0) or m, m)
+        return m, mk, (m + 2.0 * mk) / 3.0, f"{m} moduli in potrf, {mk} in trtri/lauum"
+    if mode == "digits":
+        s = eng.fp64_slices
+        sk = min(getattr(eng, "fp64_slices_kinv", 0) or s, s)
+        a, b = s * (s + 1) // 2, sk * (sk + 1) // 2
+        return a, b, (a + 2.0 * b) / 3.0, f"{s} digit planes in potrf, {sk} in trtri/lauum"
+    return 0, 0, 0.0, "pure FP64"
+
+
+def roofline_entry(eng, achieved, dmma_peak, peaks, peak_src, gemm_flops, gemm_launches, fact_ms, steps, i8_peak=None):
     """Roofline of the dominant kernel of the step (the O(n^3) factorisation layer).
 
     achieved = algorithmic q*n^3 FLOP per step / CUDA-event time of the potrf + solve + potri phases.
-    With the FP64-via-INT8 path on (default), the large GEMMs run in ozaki_gemm_kernel on the tcgen05 INT8
-    tensor path: one FP64 product = s(s+1)/2 INT8 products, so the tensor roofline is (INT8 dense rate) /
-    (s(s+1)/2); the INT8 rate is taken as twice the MEASURED bf16 rate of MEASURED_PEAKS.json (kind::i8 issues
-    at twice the kind::f16 rate).  The FP64 DMMA peak (live microbenchmark) is reported next to it."""
-    s = getattr(eng, "fp64_slices", 0)
+    With the FP64-via-INT8 path on (default), the large GEMMs run on the tcgen05 INT8 tensor path: one FP64
+    product = P INT8 products (P = moduli of the residue scheme, or s(s+1)/2 digit-plane pairs), so the tensor
+    roofline is (INT8 dense rate) / P.  `peak` uses the INT8 rate MEASURED on this GPU by plmc_peak_i8 (a
+    shared-memory-resident tcgen05.mma.kind::i8 loop on every SM pair); the figure derived from
+    MEASURED_PEAKS.json (2 x sustained bf16) is kept beside it.  The FP64 DMMA peak (live) is reported as well."""
+    main, kinv, pairs_eff, desc = products_per_fp64_product(eng)
     common = {
         "bound": "tensor", "achieved": achieved, "unit": "TFLOP/s", "traffic": None,
         "fp64_dmma_peak": dmma_peak, "vs_fp64_dmma_peak": (achieved / dmma_peak) if achieved else None,
         "executed_dmma_gemm_tflops": gemm_flops / steps / (fact_ms * 1e-3) / 1e12 if fact_ms > 0 else None,
         "dmma_gemm_launches_per_step": gemm_launches / steps,
-        "traffic_reference": "ncu --set full, one 8192^3 gemm_dmma_kernel launch: 6.77 GB read + 0.53 GB written "
-                             "(1.61 GB algorithmic) at 0.23 TB/s: not traffic bound (profiles/r01_gemm_dmma_ncu_full.txt)",
+        "how": "algorithmic q*n^3 FLOP per step / CUDA-event time of the potrf+solve+potri phases",
     }
-    if s > 0:
-        pairs = s * (s + 1) // 2
-        # potrf (1/3 of the q*n^3 FLOP) uses s slices, trtri + lauum (2/3; K^-1 feeds only the gradients)
-        # fp64_slices_kinv: the roof is taken with the flop-weighted number of INT8 products per FP64 product
-        sk = min(getattr(eng, "fp64_slices_kinv", 0) or s, s)
-        pairs_eff = (pairs + 2.0 * (sk * (sk + 1) // 2)) / 3.0
+    if pairs_eff > 0:
         bf16 = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops")
-        peak = 2.0 * bf16 / pairs_eff
+        derived = 2.0 * bf16 / pairs_eff
+        peak = (i8_peak / pairs_eff) if i8_peak else derived
+        mode = eng.emulation_mode() if hasattr(eng, "emulation_mode") else "digits"
         common.update({
-            # one ncu --set full capture of ozaki_gemm_kernel (8192^3, 7 slices): dram read 7.91 GB + write 0.60 GB
-            # per launch against 1.47 GB algorithmic (planes once + C once); re-reads are L2 misses of the
-            # streamed B planes, the kernel runs at 0.68 TB/s: not traffic bound
-            "traffic": 8.50e9,
-            "traffic_reference": "ncu --set full, one 8192^3 ozaki_gemm_kernel launch (profiles/"
-                                 "r01_ozaki_gemm_v2_ncu_summary.md): 7.91 GB read + 0.60 GB written per launch, "
-                                 "1.47 GB algorithmic, 0.68 TB/s: not traffic bound; tensor pipe (UTCIMMA) 54 % of "
-                                 "nominal, power-capped",
-            "kernel": "ozaki_gemm_kernel (FP64 GEMM as %d INT8 tcgen05.mma products, TMA + TMEM) for GEMMs >= %d; "
-                      "gemm_dmma_kernel (DMMA.8x8x4) below" % (pairs, eng.fp64_min_dim),
+            "kernel": ("rns_gemm_kernel (FP64 GEMM as %d INT8 tcgen05.mma products modulo coprime moduli, CTA pairs, "
+                       "TMEM, bulk async copies) + crt_kernel for GEMMs >= %d; gemm_dmma_kernel (DMMA.8x8x4) below"
+                       % (main, eng.fp64_min_dim)) if mode == "rns" else
+                      ("ozaki_gemm_kernel (FP64 GEMM as %d INT8 tcgen05.mma digit-plane products, TMEM, bulk async "
+                       "copies) for GEMMs >= %d; gemm_dmma_kernel (DMMA.8x8x4) below" % (main, eng.fp64_min_dim)),
             "peak": peak, "frac": (achieved / peak) if achieved else None,
-            "peak_source": "2 x %s bf16 sustained (%.0f TFLOP/s) / %.2f INT8 products per FP64 product "
-                           "(%d slices in potrf, %d in trtri/lauum, flop-weighted)" % (peak_src, bf16, pairs_eff, s, sk),
-            "how": "algorithmic q*n^3 FLOP per step / CUDA-event time of the potrf+solve+potri phases",
+            "peak_source": ("live plmc_peak_i8 (%.0f INT8 TOPS, tcgen05.mma.kind::i8 on shared-memory-resident "
+                            "operands, every SM) / %.2f INT8 products per FP64 product (%s, flop-weighted)"
+                            % (i8_peak, pairs_eff, desc)) if i8_peak else
+                           ("2 x %s bf16 sustained (%.0f TFLOP/s) / %.2f INT8 products per FP64 product (%s)"
+                            % (peak_src, bf16, pairs_eff, desc)),
+            "peak_derived_from_measured_bf16": derived,
+            "frac_of_derived_peak": (achieved / derived) if achieved else None,
+            "int8_products_per_fp64_product": pairs_eff,
         })
     else:
         common.update({
@@ -207,33 +258,78 @@ def roofline_entry(eng, achieved, dmma_peak, peaks, peak_src, gemm_flops, gemm_l
             "peak": dmma_peak, "frac": (achieved / dmma_peak) if achieved else None,
             "peak_source": "live register-resident DMMA microbenchmark on this GPU (FP64 is absent from "
                            "MEASURED_PEAKS.json)",
-            "how": "algorithmic q*n^3 FLOP per step / CUDA-event time of the potrf+solve+potri phases",
         })
     return common
 
 
-def oracle_iteration_time(cfg, n_s, steps, warmup, world=1):
-    """The reference's algorithm (Cholesky-forced gpytorch semantics, restated in oracle/) on the host cores.
-    `world` scales the model like the GPU arm does (4 latents / 7 tasks per GPU)."""
+# --------------------------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port) and the library path on the same GPU
+# --------------------------------------------------------------------------------------------------------------------
+def oracle_iteration_time(cfg, p, q, n_s, reps, warmup, device="cpu"):
+    """One training iteration (fwd + bwd + AdamW) of the reference's algorithm (Cholesky-forced gpytorch semantics,
+    restated in oracle/) on `device`; returns mean seconds per iteration."""
     from oracle import plmc_oracle as O
     from tests.helpers import oracle_params
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    X, Y = make_data(n_s, cfg["d"], cfg["p"] * world, cfg["q"] * world, seed=1)
-    m = build_model(X, Y, cfg["q"] * world, cfg["kernel"])
+    X, Y = make_data(n_s, cfg["d"], p, q, seed=1)
+    m = build_model(X, Y, q, cfg["kernel"])
+    if device != "cpu":
+        m = m.to(device)
+        X, Y = X.to(device), Y.to(device)
     times = []
     opt = torch.optim.AdamW(m.parameters(), lr=1e-2)
-    for it in range(warmup + steps):
+    for it in range(warmup + reps):
+        if device != "cpu":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
         loss = -O.mll(oracle_params(m), X, Y)
         loss.backward()
         opt.step()
+        if device != "cpu":
+            torch.cuda.synchronize()
         t1 = time.perf_counter()
         if it >= warmup:
             times.append(t1 - t0)
-    return sum(times) / len(times), cores
+    return sum(times) / len(times)
+
+
+def oracle_scaling_fit(cfg, p, q, ns, n_target, budget_s=60.0):
+    """Times the oracle at several n on all host threads, fits t = c n^e by least squares in log-log and evaluates
+    the fit at n_target.  Returns (seconds at n_target, exponent, samples [(n, s/iter)], cores)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ns = [n for n in ns if n <= n_target] or [n_target]
+    samples = []
+    for i, n_s in enumerate(ns):
+        t = oracle_iteration_time(cfg, p, q, n_s, 1, 1 if i == 0 else 0)
+        if t < budget_s / 20:      # cheap sample: average a few more
+            reps = int(min(4, max(1, (budget_s / 20) / t)))
+            t = oracle_iteration_time(cfg, p, q, n_s, reps, 0)
+        samples.append((n_s, t))
+    if len(samples) >= 2:
+        lx = [math.log(n) for n, _ in samples]
+        ly = [math.log(t) for _, t in samples]
+        mx, my = sum(lx) / len(lx), sum(ly) / len(ly)
+        e = sum((a - mx) * (b - my) for a, b in zip(lx, ly)) / sum((a - mx) ** 2 for a in lx)
+        # anchor the extrapolation at the largest measured n (the asymptotic regime), exponent from the fit
+        n_l, t_l = samples[-1]
+        t_target = t_l * (n_target / n_l) ** e
+    else:
+        e = None
+        t_target = samples[0][1]
+    return t_target, e, samples, cores
+
+
+def baseline_sample_text(cfg, p, q, samples, e, n, t_target, cores):
+    pts = ", ".join(f"n={a}: {b:.3f} s/iter" for a, b in samples)
+    if e is None:
+        return (f"oracle (pure-torch restatement of the reference's Cholesky-forced path) fwd+bwd+AdamW measured at the "
+                f"full n={n} (d={cfg['d']}, p={p}, q={q}, {cfg['kernel']}) on {cores} host threads: {pts}")
+    return (f"oracle (pure-torch restatement of the reference's Cholesky-forced path; gpytorch is not installable) "
+            f"fwd+bwd+AdamW at d={cfg['d']}, p={p}, q={q}, {cfg['kernel']} on {cores} host threads: {pts}; fitted "
+            f"t ~ n^{e:.2f}; EXTRAPOLATED from the largest sample with that exponent to n={n}: {t_target:.1f} s/iter "
+            f"(a full-size CPU iteration would take hours and ~4x the Gram storage in autograd temporaries)")
 
 
 def run_reference(args, cfg):
@@ -241,38 +337,117 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     n = args.n or cfg["n"]
-    n_s = min(CPU_SAMPLE_N, n)
-    world = max(1, args.gpus)
-    t, cores = oracle_iteration_time(cfg, n_s, max(1, args.steps), max(1, min(args.warmup, 1)), world)
-    scale = (n_s / n) ** 3
-    value = (world / t) * scale          # one step of the N-GPU workload = N four-latent model iterations
-    sample = (f"oracle (pure-torch restatement of the reference's Cholesky-forced path; gpytorch is not installable) "
-              f"fwd+bwd at n={n_s}, d={cfg['d']}, p={cfg['p'] * world}, q={cfg['q'] * world}, {cfg['kernel']}: "
-              f"{t:.3f} s/iter on {cores} host threads; it/s scaled by (n_s/n)^3 = {scale:.3e} to n={n}")
+    # the reference arm times ONE model of the per-GPU shape on this host, whatever N is: a CPU box does not grow
+    # with the GPU count, and the GPU arm's `value` counts models of exactly this shape
+    p, q = (cfg["named_p"], cfg["named_q"]) if args.scaling == "strong" else (cfg["p"], cfg["q"])
+    steps = args.steps or cfg["steps"]
+    t, e, samples, cores = oracle_scaling_fit(cfg, p, q, REFERENCE_FIT_NS, n, budget_s=90.0)
+    value = 1.0 / t
+    sample = baseline_sample_text(cfg, p, q, samples, e, n, t, cores)
     line = {
         "impl": "reference", "metric": "train_iters_per_sec", "value": value, "unit": "it/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * world / value, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 / value, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, cfg, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample,
+                         "fitted_exponent": e, "samples_n_seconds": samples, "extrapolated": e is not None},
         "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "value is for ONE model of the per-GPU shape on the host cores (not multiplied by the GPU count)",
     }
     print(json.dumps(line), flush=True)
 
 
 def workload_config(args, cfg, world):
     n = args.n or cfg["n"]
-    return {
+    scaling = getattr(args, "scaling", "weak")
+    p_tot, q_tot = model_shape(cfg, world, scaling)
+    q_loc = -(-q_tot // world)
+    out = {
         "workload": f"{cfg['label']}: n={n}, d={cfg['d']}, {cfg['kernel']} ARD, fp64, PLMC variant (BDN=False), "
-                    f"{cfg['q']} latents and {cfg['p']} tasks per GPU",
-        "n": n, "d": cfg["d"], "tasks_total": cfg["p"] * world, "latents_total": cfg["q"] * world,
-        "latents_per_gpu": cfg["q"], "parallelism": f"latent-parallel x{world}",
+                    f"{q_tot} latents and {p_tot} tasks on {world} GPU(s) ({q_loc} latents per GPU)",
+        "n": n, "d": cfg["d"], "tasks_total": p_tot, "latents_total": q_tot,
+        "latents_per_gpu": q_loc, "parallelism": f"latent-parallel x{world}",
         "step": "zero_grad + MLL forward + full backward + AdamW step + LR scheduler step (experiments.py:263-273)",
-        "value_definition": "iterations/s of a 4-latent model of this shape; one step at N GPUs = N of them",
-        "l2_policy": "inputs larger than L2 (K is %.1f GB per GPU)" % (cfg["q"] * n * n * 8 / 1e9),
+        "value_definition": ("iterations/s of the named model (fixed size, latents split over the GPUs)"
+                             if scaling == "strong" else
+                             f"iterations/s of a {cfg['q']}-latent / {cfg['p']}-task model of this shape; one step at N "
+                             f"GPUs = N of them"),
+        "l2_policy": "inputs larger than L2 (K is %.1f GB per GPU)" % (q_loc * n * n * 8 / 1e9),
     }
+    if n * n * 8 * q_loc < 200e6:
+        out["l2_policy"] = "L2 flushed between timed iterations (a 256 MB buffer is rewritten; K is %.0f MB)" % (
+            q_loc * n * n * 8 / 1e6)
+    return out
 
 
+def timed_calls(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3
+
+
+def secondary_kernels(model, cfg, n, q_loc, phases, steps, peaks, peak_src):
+    """HBM-bound kernels of the step against the measured copy bandwidth: Gram build and gradient sweep from the
+    phase events of the timed steps, the projection kernels timed alone (workload shape, and a shape large enough
+    to leave L2)."""
+    from projected_lmc_b200 import ops
+
+    hbm = peaks.get("hbm_gbs")
+    np_ = ((n + 127) // 128) * 128
+    gram_bytes = 8.0 * q_loc * np_ * (np_ + 128) / 2
+    out = []
+
+    def entry(kernel, nbytes, seconds, note=None):
+        ach = nbytes / seconds / 1e9 if seconds and seconds > 0 else None
+        e = {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": hbm, "peak_source": peak_src, "unit": "GB/s",
+             "frac": (ach / hbm) if (ach and hbm) else None, "bytes": nbytes, "seconds": seconds}
+        if note:
+            e["note"] = note
+        out.append(e)
+
+    entry("gram_kernel (fused ARD Gram build, lower tiles written once)", gram_bytes,
+          phases.get("gram", 0.0) / steps * 1e-3)
+    entry("grad_sweep_kernel (fused backward sweep over the lower tiles of K^-1)", gram_bytes,
+          phases.get("grad_sweep", 0.0) / steps * 1e-3)
+    Y = model.train_y
+    p = Y.shape[1]
+    q = model.n_latents
+    dev = Y.device
+    T = torch.randn(p, q, dtype=torch.float64, device=dev)
+    G = torch.randn(q, n, dtype=torch.float64, device=dev)
+    pj = 8.0 * n * (p + q)
+    entry("project_fwd_kernel (workload shape)", pj, timed_calls(lambda: ops.project_fwd(Y, T), 20),
+          "Y is %.1f MB: L2-resident and launch-latency bound at this size" % (Y.numel() * 8 / 1e6))
+    entry("project_bwd_kernel + reduce (workload shape)", pj, timed_calls(lambda: ops.project_bwd(Y, G), 20))
+    nb, pb, qb = 4000000, 32, 8                                   # 1.28 GB: streams from HBM
+    Yb = torch.randn(nb, pb, dtype=torch.float64, device=dev)
+    Tb = torch.randn(pb, qb, dtype=torch.float64, device=dev)
+    Gb = torch.randn(qb, nb, dtype=torch.float64, device=dev)
+    entry("project_fwd_kernel (n=4e6, p=32, q=8)", 8.0 * nb * (pb + qb), timed_calls(lambda: ops.project_fwd(Yb, Tb), 5))
+    entry("project_bwd_kernel + reduce (n=4e6, p=32, q=8)", 8.0 * nb * (pb + qb),
+          timed_calls(lambda: ops.project_bwd(Yb, Gb), 5))
+    return out
+
+
+def library_baseline(cfg, n_lib):
+    """The same restatement the CPU arm times, on THIS GPU through torch -> cuSOLVER/cuBLAS (cholesky_ex,
+    solve_triangular, autograd): the "library path on the same box" of SURVEY section 2."""
+    try:
+        t = oracle_iteration_time(cfg, cfg["p"], cfg["q"], n_lib, 2, 1, device="cuda")
+        return {"n": n_lib, "seconds_per_iter": t, "it_per_s": 1.0 / t,
+                "what": "oracle restatement on cuda: torch.linalg.cholesky_ex / solve_triangular / autograd "
+                        "(cuSOLVER + cuBLAS), same d, p, q, kernel"}
+    except Exception as ex:  # noqa: BLE001
+        return {"n": n_lib, "error": repr(ex)[:300]}
+
+
+# --------------------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
     cfg = WORKLOADS[args.workload]
@@ -290,15 +465,31 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.workload == "c3":
+        run_predict_workload(args, cfg, world, rank, dev)
+    else:
+        run_train_workload(args, cfg, world, rank, dev)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_train_workload(args, cfg, world, rank, dev):
+    import torch.distributed as dist
+
     from projected_lmc_b200 import ProjectedLMCmll, distributed as pdist, ops
 
     n = args.n or cfg["n"]
-    p_tot, q_tot = cfg["p"] * world, cfg["q"] * world
+    steps = args.steps or cfg["steps"]
+    p_tot, q_tot = model_shape(cfg, world, args.scaling)
+    if q_tot < world:
+        raise SystemExit(f"{args.workload}: {q_tot} latents cannot be split over {world} GPUs (DESIGN.md section 4)")
     Xh, Yh = make_data(n, cfg["d"], p_tot, q_tot, seed=0)
     Xh, Yh = Xh.pin_memory(), Yh.pin_memory()
-    model = build_model(Xh.clone(), Yh.clone(), q_tot, cfg["kernel"]).cuda()
+    model = build_model(Xh.clone(), Yh.clone(), q_tot, cfg["kernel"]).to(dev)
     if world > 1:
         pdist.shard_latents(model, rank, world)
+    lo, hi = model._latent_range
+    q_loc = hi - lo
     model.train()
     mll = ProjectedLMCmll(model.likelihood, model)
     Xd, Yd = model.train_inputs[0], model.train_y
@@ -307,6 +498,8 @@ def main():
     # optimiser and schedule of the reference's training loop (experiments.py:79-86, 240, 251, 263-273)
     opt = torch.optim.AdamW(params, lr=1e-2)
     sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=math.exp(math.log(1e-3 / 1e-2) / 10000))
+    small = n * n * 8 * q_loc < 200e6
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
 
     def step():
         opt.zero_grad(set_to_none=True)
@@ -322,56 +515,75 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index)
     sampler.start()
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         step()
     peak = dmma_peak_tflops()
+    i8_peak = i8_peak_tops()
 
     # ---- timed region: device-resident inputs --------------------------------------
     eng = model._engine
     barrier()
     t_wall0 = time.time()
-    eng.profile = []
     ops.stats_reset()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        loss = step()
-    e1.record()
-    barrier()
+    if small:
+        # launch-bound regime: per-step events, L2 flushed (untimed) between the steps
+        eng.profile = None
+        per = []
+        for _ in range(steps):
+            flush_buf.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss = step()
+            e1.record()
+            per.append((e0, e1))
+        barrier()
+        total_ms = sum(a.elapsed_time(b) for a, b in per)
+        phases = {}
+    else:
+        eng.profile = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = step()
+        e1.record()
+        barrier()
+        total_ms = e0.elapsed_time(e1)
+        phases = eng.phase_ms()
+        eng.profile = None
     clocks = sampler.stop(t_wall0, time.time())
     launches, gemm_launches, gemm_flops = ops.stats_get()
-    phases = eng.phase_ms()
-    eng.profile = None
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    ms = torch.tensor([total_ms / steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms.item())
-    value = world / (ms_per_step * 1e-3)
+    models_per_step = 1 if args.scaling == "strong" else world
+    value = models_per_step / (ms_per_step * 1e-3)
 
     # ---- end to end: host buffers in, loss out, every step -------------------------
     e2e = None
     if not args.no_e2e:
         barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             Xd.copy_(Xh, non_blocking=True)
             Yd.copy_(Yh, non_blocking=True)
             lv = step()
             _ = float(lv.item())
         e1.record()
         barrier()
-        ms2 = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        ms2 = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
         if world > 1:
             dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        e2e = {"value": world / (float(ms2.item()) * 1e-3), "unit": "it/s",
+        e2e = {"value": models_per_step / (float(ms2.item()) * 1e-3), "unit": "it/s",
                "h2d_bytes_per_step": (Xh.numel() + Yh.numel()) * 8, "d2h_bytes_per_step": 8}
 
     # ---- prediction: batched predictive mean/variance on the same model (secondary metric) -------
     predict = None
     if not args.no_predict:
-        n_test = args.test_points
+        n_test = args.test_points or (8192 if not small else 4096)
         gt = torch.Generator().manual_seed(7)
         Xs = (torch.rand(n_test, cfg["d"], generator=gt, dtype=torch.float64) * 2 - 1).to(dev)
         model.eval()
@@ -399,54 +611,175 @@ def main():
         pred_s = float(ms3.item()) * 1e-3
         predict = {"points_per_sec": n_test / pred_s, "n_test": n_test, "seconds": pred_s,
                    "factorisation_seconds_excluded": fact_s, "checksum": chk,
-                   "algorithmic_tflops": cfg["q"] * float(n) ** 2 * n_test / pred_s / 1e12,
+                   "algorithmic_tflops": q_loc * float(n) ** 2 * n_test / pred_s / 1e12,
                    "note": "mean + variance [n_test, tasks] through model.eval(); full_likelihood(model(X*)); "
                            "FLOP = q*n^2*n* (triangular solve), per GPU"}
         model.train()
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        q_loc = cfg["q"]
-        fact_ms = sum(phases.get(k, 0.0) for k in ("potrf", "retry", "solve_logdet", "potri")) / args.steps
+        fact_ms = sum(phases.get(k, 0.0) for k in ("potrf", "retry", "solve_logdet", "potri")) / steps
         alg_flops = q_loc * float(n) ** 3                       # n^3/3 potrf + 2n^3/3 inverse, per GPU
         achieved = alg_flops / (fact_ms * 1e-3) / 1e12 if fact_ms > 0 else None
-        np_ = ((n + 127) // 128) * 128
-        gram_bytes = 8.0 * q_loc * np_ * (np_ + 128) / 2
         line = {
-            "metric": "train_iters_per_sec", "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, cfg, world),
+            "metric": "train_iters_per_sec", "value": value, "unit": "it/s", "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, cfg, world),
             "loss": float(loss.item()),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "arithmetic": {"gemm_mode": eng.emulation_mode(), "min_dim": eng.fp64_min_dim,
+                           "int8_products": products_per_fp64_product(eng)[3]},
             "roofline": roofline_entry(eng, achieved, peak, peaks, peak_src, gemm_flops, gemm_launches, fact_ms,
-                                       args.steps),
-            "roofline_secondary": [{
-                "kernel": "gram_kernel (fused ARD Gram build)", "bound": "hbm",
-                "achieved": gram_bytes / (phases.get("gram", 0.0) / args.steps * 1e-3) / 1e9 if phases.get("gram") else None,
-                "peak": peaks.get("hbm_gbs"), "peak_source": peak_src, "unit": "GB/s",
-            }, {
-                "kernel": "grad_sweep_kernel (fused backward sweep)", "bound": "hbm",
-                "achieved": gram_bytes / (phases.get("grad_sweep", 0.0) / args.steps * 1e-3) / 1e9 if phases.get("grad_sweep") else None,
-                "peak": peaks.get("hbm_gbs"), "peak_source": peak_src, "unit": "GB/s",
-            }],
-            "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+                                       steps, i8_peak),
+            "phase_ms_per_step": {k: v / steps for k, v in phases.items()},
             "predict": predict,
         }
-        for r in line["roofline_secondary"]:
-            r["frac"] = (r["achieved"] / r["peak"]) if (r["achieved"] and r["peak"]) else None
-        if world == 1 and not args.no_cpu_baseline:
-            del model, mll
-            n_s = min(CPU_SAMPLE_N, n)
-            t, cores = oracle_iteration_time(cfg, n_s, 2, 1)
-            scale = (n_s / n) ** 3
-            line["cpu_baseline"] = {
-                "value": (1.0 / t) * scale, "unit": "it/s", "cores": cores, "kind": "port",
-                "sample": f"oracle fwd+bwd at n={n_s} (same d, p, q, kernel): {t:.3f} s/iter on {cores} host threads; "
-                          f"it/s scaled by (n_s/n)^3 = {scale:.3e} to n={n}",
-            }
+        if small:
+            line["roofline"]["note"] = ("launch-bound configuration: n=%d gives a %.0f MFLOP factorisation per latent; "
+                                        "the step time is kernel-launch latency, not tensor throughput" % (n, n ** 3 / 1e6))
+        if not args.no_secondary and not small:
+            line["roofline_secondary"] = secondary_kernels(model, cfg, n, q_loc, phases, steps, peaks, peak_src)
+            if predict:
+                line["roofline_secondary"].append({
+                    "kernel": "prediction: cross-Gram + TRSM (L^-1 K*) on the INT8 tensor path + column reductions",
+                    "bound": "tensor", "achieved": predict["algorithmic_tflops"], "unit": "TFLOP/s",
+                    "peak": line["roofline"].get("peak") and i8_peak / products_per_fp64_product(eng)[0]
+                    if products_per_fp64_product(eng)[0] else peak,
+                    "how": "q*n^2*n* FLOP / CUDA-event time of model(X*) + full_likelihood, n* = %d" % predict["n_test"]})
+                r = line["roofline_secondary"][-1]
+                r["frac"] = (r["achieved"] / r["peak"]) if r.get("peak") else None
+        if world == 1:
+            del model, mll, opt
+            eng.release()
+            torch.cuda.empty_cache()
+            if not args.no_library_baseline and not small:
+                line["library_baseline"] = library_baseline(cfg, min(LIBRARY_N, n))
+            if not args.no_cpu_baseline:
+                t, e, samples, cores = oracle_scaling_fit(cfg, cfg["p"], cfg["q"], CPU_FIT_NS, n, budget_s=20.0)
+                line["cpu_baseline"] = {
+                    "value": 1.0 / t, "unit": "it/s", "cores": cores, "kind": "port",
+                    "sample": baseline_sample_text(cfg, cfg["p"], cfg["q"], samples, e, n, t, cores),
+                    "fitted_exponent": e, "samples_n_seconds": samples, "extrapolated": e is not None,
+                }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+
+
+def run_predict_workload(args, cfg, world, rank, dev):
+    """C3: batched predictive mean / variance for n_test points.  Test points are sharded over the ranks (no
+    per-point communication); every rank factorises all q latents once (not timed in `value`, reported beside it)."""
+    import torch.distributed as dist
+
+    from projected_lmc_b200 import ops
+
+    n = args.n or cfg["n"]
+    n_test = args.test_points or cfg["n_test"]
+    steps = args.steps or cfg["steps"]
+    p, q = cfg["named_p"], cfg["named_q"]
+    Xh, Yh = make_data(n, cfg["d"], p, q, seed=0)
+    model = build_model(Xh, Yh, q, cfg["kernel"]).to(dev)
+    model.eval()
+    lo = rank * n_test // world
+    hi = (rank + 1) * n_test // world
+    gt = torch.Generator().manual_seed(7)
+    Xs_h = (torch.rand(n_test, cfg["d"], generator=gt, dtype=torch.float64) * 2 - 1)[lo:hi].contiguous().pin_memory()
+    mean_h = torch.empty((hi - lo, p), dtype=torch.float64).pin_memory()
+    var_h = torch.empty((hi - lo, p), dtype=torch.float64).pin_memory()
+    chunk = 65536
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        _ = model(Xs_h[:128].to(dev))                # factorisation of all q latents (cached)
+        e1.record()
+        barrier()
+        fact_s = e0.elapsed_time(e1) * 1e-3
+        full_lik = model.full_likelihood()
+        Xs_d = Xs_h.to(dev)
+        for _ in range(max(1, min(args.warmup, 2))):
+            _ = full_lik(model(Xs_d[:8192]))
+        i8_peak = i8_peak_tops()
+        peak = dmma_peak_tflops()
+        eng = model._engine
+
+        def run(from_host):
+            chk = torch.zeros((), dtype=torch.float64, device=dev)
+            for s0 in range(0, hi - lo, chunk):
+                s1 = min(hi - lo, s0 + chunk)
+                xs = Xs_h[s0:s1].to(dev, non_blocking=True) if from_host else Xs_d[s0:s1]
+                pred = full_lik(model(xs))
+                if from_host:
+                    mean_h[s0:s1].copy_(pred.mean, non_blocking=True)
+                    var_h[s0:s1].copy_(pred.variance, non_blocking=True)
+                chk = chk + pred.mean.sum() + pred.variance.sum()
+            return chk
+
+        barrier()
+        t_wall0 = time.time()
+        ops.stats_reset()
+        e0.record()
+        for _ in range(steps):
+            chk = run(False)
+        e1.record()
+        barrier()
+        clocks = sampler.stop(t_wall0, time.time())
+        launches, gemm_launches, gemm_flops = ops.stats_get()
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sec = float(ms.item()) * 1e-3
+        e2e = None
+        if not args.no_e2e:
+            barrier()
+            e0.record()
+            for _ in range(steps):
+                chk2 = run(True)
+                _ = float(chk2.item())
+            e1.record()
+            barrier()
+            ms2 = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+            if world > 1:
+                dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+            e2e = {"value": n_test / (float(ms2.item()) * 1e-3), "unit": "points/s",
+                   "h2d_bytes_per_step": n_test * cfg["d"] * 8, "d2h_bytes_per_step": 2 * n_test * p * 8 + 8 * world}
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        main = products_per_fp64_product(eng)[0]
+        alg = q * float(n) ** 2 * (hi - lo) / sec / 1e12
+        rpeak = (i8_peak / main) if main else peak
+        line = {
+            "metric": "predict_points_per_sec", "value": n_test / sec, "unit": "points/s", "n_gpus": world,
+            "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{cfg['label']}: n_test={n_test} points sharded over {world} GPU(s), train n={n}, "
+                                   f"d={cfg['d']}, {p} tasks, {q} latents, {cfg['kernel']} ARD, fp64; every rank holds "
+                                   f"all {q} Cholesky factors ({q * n * n * 8 / 1e9:.1f} GB)",
+                       "n": n, "n_test": n_test, "d": cfg["d"], "tasks_total": p, "latents_total": q,
+                       "parallelism": f"test-point-parallel x{world} (no collective on the data path)",
+                       "step": "predictive mean + variance [n_test, tasks] through model.eval(); full_likelihood(model(X*))",
+                       "l2_policy": "inputs larger than L2 (the factors are %.1f GB per GPU)" % (q * n * n * 8 / 1e9)},
+            "factorisation_seconds_excluded": fact_s, "checksum": float(chk.item()),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "arithmetic": {"gemm_mode": eng.emulation_mode(), "min_dim": eng.fp64_min_dim,
+                           "int8_products": products_per_fp64_product(eng)[3]},
+            "roofline": {"bound": "tensor", "achieved": alg, "peak": rpeak, "unit": "TFLOP/s",
+                         "frac": alg / rpeak if rpeak else None, "traffic": None,
+                         "kernel": "triangular solve L^-1 K* of the predictive variance (q n^2 n* FLOP per rank) on the "
+                                   "INT8 tensor path",
+                         "peak_source": "live plmc_peak_i8 (%.0f INT8 TOPS) / %d INT8 products per FP64 product"
+                                        % (i8_peak, main) if main else "live DMMA microbenchmark",
+                         "fp64_dmma_peak": peak},
+        }
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

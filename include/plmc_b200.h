@@ -62,6 +62,12 @@ typedef struct plmc_gemm_cfg {
     int precision;
     int min_dim; /* >= 128 */
     int flags;
+    /* mode PLMC_GEMM_INT8_RNS only: the residue scheme pays a fixed cost per output element (residues out,
+     * reconstruction in), so products with a short inner dimension or little work run on digit planes instead:
+     * K < rns_min_k or M*N*K < rns_min_mnk -> PLMC_GEMM_INT8_DIGITS with alt_precision planes (0: always RNS). */
+    int alt_precision;
+    int rns_min_k;
+    long long rns_min_mnk;
 } plmc_gemm_cfg;
 
 int plmc_version(void);

@@ -40,7 +40,7 @@ static bool make_ctx(LaCtx& cx, cudaStream_t st, int batch, const plmc_gemm_cfg*
     if (cfg->mode == PLMC_GEMM_INT8_DIGITS) {
         if (cfg->precision < 1 || cfg->precision > 7) return false;
     } else if (cfg->mode == PLMC_GEMM_INT8_RNS) {
-        if (cfg->precision < 8 || cfg->precision > 18) return false;
+        if (cfg->precision < 8 || cfg->precision > 18 || cfg->alt_precision < 0 || cfg->alt_precision > 7) return false;
     } else {
         return false;
     }
@@ -51,6 +51,11 @@ static bool make_ctx(LaCtx& cx, cudaStream_t st, int batch, const plmc_gemm_cfg*
     cx.oz_prec = cfg->precision;
     cx.oz_min = cfg->min_dim;
     cx.oz_flags = cfg->flags;
+    if (cfg->mode == PLMC_GEMM_INT8_RNS) {
+        cx.oz_alt = cfg->alt_precision;
+        cx.oz_rns_min_k = cfg->rns_min_k;
+        cx.oz_rns_min_mnk = cfg->rns_min_mnk;
+    }
     return true;
 }
 

@@ -95,15 +95,21 @@ static void gemm_impl(LaCtx& cx, bool aKC, bool bKC, BMat A, BMat B, BMat C, int
         // large update: FP64 product through the INT8 tensor path (all batch members per launch when
         // the plane scratch holds them, otherwise in passes; everything is ordered on the one stream)
         const bool same = (A.p == B.p && A.ld == B.ld && aKC == bKC && M == N);
-        if (cx.oz_mode == 2) {   // residue planes: a product that does not fit the scratch is split inside
+        int prec = cx.oz_prec;
+        bool rns = (cx.oz_mode == 2);
+        if (rns && cx.oz_alt > 0 && (K < cx.oz_rns_min_k || (long long)M * N * K < cx.oz_rns_min_mnk)) {
+            rns = false;   // short inner dimension / little work: digit planes have the lower per-element cost
+            prec = cx.oz_alt;
+        }
+        if (rns) {   // residue planes: a product that does not fit the scratch is split inside
             cx.status = rns_gemm(aKC, bKC, A.p, A.ld, A.stride, B.p, B.ld, B.stride, C.p, C.ld, C.stride, M, N, K, alpha,
                                  beta, lower, cx.oz_prec, same, cx.batch, cx.oz_ws, cx.oz_bytes, cx.oz_flags, cx.st);
             *path = 1;
             return;
         }
-        if (ozaki_ws_bytes(M, N, K, cx.oz_prec, same) + 1024 <= cx.oz_bytes) {
+        if (ozaki_ws_bytes(M, N, K, prec, same) + 1024 <= cx.oz_bytes) {
             cx.status = ozaki_gemm(aKC, bKC, A.p, A.ld, A.stride, B.p, B.ld, B.stride, C.p, C.ld, C.stride, M, N, K,
-                                   alpha, beta, lower, cx.oz_prec, same, cx.batch, cx.oz_ws, cx.oz_bytes, cx.st);
+                                   alpha, beta, lower, prec, same, cx.batch, cx.oz_ws, cx.oz_bytes, cx.st);
             *path = 1;
             return;
         }

@@ -32,6 +32,10 @@ struct LaCtx {
     int oz_prec = 0;
     int oz_min = 1024;  // smallest M, N, K routed to the INT8 path
     int oz_flags = 0;   // bit 0: single-CTA kernel in mode 2
+    // mode 2: digit planes (oz_alt slices) for products with K < oz_rns_min_k or M N K < oz_rns_min_mnk
+    int oz_alt = 0;
+    int oz_rns_min_k = 0;
+    long long oz_rns_min_mnk = 0;
 };
 
 // per-device one-time state (function attributes, SM count): indexed by the CUDA device ordinal

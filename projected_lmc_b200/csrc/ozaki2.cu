@@ -71,12 +71,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+// Arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  RELAXED on purpose: a
+// release at cluster scope compiles to MEMBAR.ALL.GPU (+ the waiter's acquire to CCTL.IVALL), ~1 us per k-stage in
+// the relay -- measured: the CTA-pair kernel ran at half the rate of the single-CTA one.  No generic-proxy data
+// is published through these barriers: what they order is async-proxy work that has already completed when the
+// arrive is issued (the bulk copy behind the local full barrier; tcgen05.ld behind tcgen05.wait::ld), exactly as
+// when a 2-SM TMA load signals the leader's barrier directly.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar), "r"(rank)
+        "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(bar), "r"(rank)
         : "memory");
 }
 // Spin on a phase parity.  A protocol bug must not hang the GPU: after ~4 s of polling the kernel traps.
@@ -487,13 +492,13 @@ __global__ void __launch_bounds__(THREADS, 1) rns_gemm_kernel(const GemmArgs2 p)
         for (int w = cluster_id; w < p.total; w += nclusters, ++nt) {
             const int buf = nt & 1, use = nt >> 1;
             if (use > 0) {   // the epilogue warps (of both CTAs) must have drained this accumulator
-                mbar_wait<CG == 2>(smem_u32(&acc_empty[buf]), (use - 1) & 1);
+                mbar_wait<false>(smem_u32(&acc_empty[buf]), (use - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             for (int kt = 0; kt < nkt; ++kt, ++it) {
                 const int st = it % C::NST, round = it / C::NST;
                 mbar_wait<false>(smem_u32(&full_bar[st]), round & 1);
-                if (CG == 2) mbar_wait<true>(smem_u32(&peer_full[st]), round & 1);
+                if (CG == 2) mbar_wait<false>(smem_u32(&peer_full[st]), round & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint32_t sa = smem0 + (uint32_t)st * C::STAGE;
@@ -605,7 +610,10 @@ __device__ __forceinline__ double pow2i(int e) {   // 2^e for e in [-1022, 1023]
     return __longlong_as_double((long long)(e + 1023) << 52);
 }
 
-// one CTA per 256 x 256 residue tile; a warp covers one row (32 lanes x 8 columns) per pass
+// One CTA per 32 rows of a 256 x 256 residue tile (gridDim.y = 8): a warp covers one row per pass (32 lanes x 8
+// columns) and 4 rows in all.  Every residue load of a row (one 8-byte word per modulus) and the old C values are
+// issued before the first use, so a warp keeps nmod + 4 independent requests in flight: the kernel is
+// HBM-bound (16 B of residues + 16 B of C per element), not latency-bound.
 __global__ void __launch_bounds__(256) crt_kernel(const CrtArgs a) {
     int tm, tn;
     if (a.lower) {
@@ -627,41 +635,54 @@ __global__ void __launch_bounds__(256) crt_kernel(const CrtArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) fb[j] = pow2i(max(a.eb[(long long)bz * a.N + gc0 + j], -1022));
     double* Cb = a.C + (long long)bz * a.sC;
-    for (int row = warp; row < 256; row += 8) {
+    const bool rmw = (a.beta != 0.0);
+#pragma unroll 1
+    for (int rr = 0; rr < 4; ++rr) {
+        const int row = blockIdx.y * 32 + warp * 4 + rr;
         const int gr = tm * 256 + row;
         if (gr >= a.M) break;
         if (a.lower && (gc0 >> 7) > (gr >> 7)) continue;
         const uint8_t* src = tile + row * 256;
+        uint2 v[MAXMOD];
+#pragma unroll
+        for (int i = 0; i < MAXMOD; ++i)
+            if (i < a.nmod) v[i] = __ldcs(reinterpret_cast<const uint2*>(src + (long long)i * a.sRm));
+        double* crow = Cb + (long long)gr * a.ldc + gc0;
+        double2 old[4];
+        if (rmw) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) old[j] = *reinterpret_cast<const double2*>(crow + 2 * j);
+        }
         double s1[8], s2[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.0;
-        for (int i = 0; i < a.nmod; ++i) {
-            const uint2 v = *reinterpret_cast<const uint2*>(src + (long long)i * a.sRm);
-            const double h = a.H[i], l = a.L[i];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int r = (int)(int8_t)(((j < 4) ? v.x : v.y) >> (8 * (j & 3)));
-                // exact int -> double: 2^52 + 2^31 + r is representable, subtract the bias
-                const double d = __hiloint2double(0x43300000, r ^ 0x80000000) - 4503601774854144.0;
-                s1[j] = fma(d, h, s1[j]);   // exact: 8-bit r times 40-bit h, at most 18 terms
-                s2[j] = fma(d, l, s2[j]);
+        for (int i = 0; i < MAXMOD; ++i) {
+            if (i < a.nmod) {
+                const double h = a.H[i], l = a.L[i];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = (int)(int8_t)(((j < 4) ? v[i].x : v[i].y) >> (8 * (j & 3)));
+                    // exact int -> double: 2^52 + 2^31 + r is representable, subtract the bias
+                    const double d = __hiloint2double(0x43300000, r ^ 0x80000000) - 4503601774854144.0;
+                    s1[j] = fma(d, h, s1[j]);   // exact: 8-bit r times 40-bit h, at most 18 terms
+                    s2[j] = fma(d, l, s2[j]);
+                }
             }
         }
         const double sa = a.alpha * a.pscale * pow2i(max(a.ea[(long long)bz * a.M + gr], -1022));
-        double* crow = Cb + (long long)gr * a.ldc + gc0;
         double out[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            double v = (s1[j] - rint(s1[j])) + s2[j];   // c'/P modulo 1
-            v -= rint(v);                                // in [-1/2, 1/2]
-            out[j] = v * sa * fb[j];
+            double v2 = (s1[j] - rint(s1[j])) + s2[j];   // c'/P modulo 1
+            v2 -= rint(v2);                               // in [-1/2, 1/2]
+            out[j] = v2 * sa * fb[j];
         }
-        if (a.beta != 0.0) {
+        if (rmw) {
 #pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-                const double2 o = *reinterpret_cast<const double2*>(crow + j);
-                out[j] = fma(a.beta, o.x, out[j]);
-                out[j + 1] = fma(a.beta, o.y, out[j + 1]);
+            for (int j = 0; j < 4; ++j) {
+                out[2 * j] = fma(a.beta, old[j].x, out[2 * j]);
+                out[2 * j + 1] = fma(a.beta, old[j].y, out[2 * j + 1]);
             }
         }
 #pragma unroll
@@ -885,7 +906,7 @@ static int rns_gemm_fit(bool aKC, bool bKC, const double* A, long long lda, long
         c.M = M; c.N = N; c.lower = lower; c.nmod = nmod;
         c.alpha = alpha; c.beta = beta;
         crt_constants(nmod, bits, c);
-        crt_kernel<<<dim3((unsigned)slots, 1, bc), 256, 0, st>>>(c);
+        crt_kernel<<<dim3((unsigned)slots, 8, bc), 256, 0, st>>>(c);
         PLMC_CHECK_LAUNCH();
         note_launch(same_operand ? 3 : 4);
     }

@@ -86,6 +86,10 @@ class LatentEngine:
     fp64_slices_kinv = int(__import__("os").environ.get("PLMC_FP64_SLICES_KINV", "6"))
     rns_moduli_kinv = int(__import__("os").environ.get("PLMC_RNS_MODULI_KINV", "14"))
     rns_flags = int(__import__("os").environ.get("PLMC_RNS_FLAGS", "0"))
+    # the residue scheme pays a fixed cost per output element: products with K < rns_min_k or M*N*K < rns_min_mnk
+    # run on digit planes of the matching grade (fp64_slices / fp64_slices_kinv) instead; 0 = residues everywhere
+    rns_min_k = int(__import__("os").environ.get("PLMC_RNS_MIN_K", "1024"))
+    rns_min_mnk = int(float(__import__("os").environ.get("PLMC_RNS_MIN_MNK", "2e10")))
     scratch_cap_bytes = int(float(__import__("os").environ.get("PLMC_SCRATCH_GB", "48")) * (1 << 30))
 
     def emulation_mode(self):
@@ -96,7 +100,7 @@ class LatentEngine:
     def _configure_fp64(self, device, np_, q=1):
         mode, md = self.emulation_mode(), self.fp64_min_dim
         key = (mode, md, self.fp64_slices, self.fp64_slices_kinv, self.rns_moduli, self.rns_moduli_kinv,
-               self.rns_flags, str(device), np_, q)
+               self.rns_flags, self.rns_min_k, self.rns_min_mnk, str(device), np_, q)
         if key == self._cfg_key:
             return
         self._cfg_key = key
@@ -108,7 +112,8 @@ class LatentEngine:
             # planes + residue tiles of the largest product of the recursion (the top-level SYRK) per latent;
             # a product that does not fit is split inside the library, batch members are processed in passes
             m = self.rns_moduli
-            per_member = m * h * h + m * (h + 256) * (h + 256) // 2 + m * h * 8192 + (1 << 20)
+            per_member = max(m * h * h + m * (h + 256) * (h + 256) // 2 + m * h * 8192,
+                             self.fp64_slices * h * (h + 8192)) + (1 << 20)
         else:
             # digit planes of the largest GEMM (s * (M + N) * K bytes, M, K <= npad/2, N <= npad/2 or a
             # prediction tile); a GEMM whose planes do not fit falls back to the DMMA kernel
@@ -124,8 +129,12 @@ class LatentEngine:
             self._oz = torch.empty((need,), dtype=torch.uint8, device=device)
         if mode == "rns":
             mk = min(self.rns_moduli_kinv or self.rns_moduli, self.rns_moduli)
-            self._cfg = (ops.gemm_cfg(self._oz, ops.GEMM_INT8_RNS, self.rns_moduli, md, self.rns_flags),
-                         ops.gemm_cfg(self._oz, ops.GEMM_INT8_RNS, mk, md, self.rns_flags))
+            alt = self.fp64_slices if (self.rns_min_k > 0 or self.rns_min_mnk > 0) else 0
+            altk = min(self.fp64_slices_kinv or alt, alt)
+            self._cfg = (ops.gemm_cfg(self._oz, ops.GEMM_INT8_RNS, self.rns_moduli, md, self.rns_flags, alt,
+                                      self.rns_min_k, self.rns_min_mnk),
+                         ops.gemm_cfg(self._oz, ops.GEMM_INT8_RNS, mk, md, self.rns_flags, altk,
+                                      self.rns_min_k, self.rns_min_mnk))
         else:
             sk = min(self.fp64_slices_kinv or self.fp64_slices, self.fp64_slices)
             self._cfg = (ops.gemm_cfg(self._oz, ops.GEMM_INT8_DIGITS, self.fp64_slices, md),
