@@ -40,8 +40,8 @@ extern "C" {
 #define PLMC_KERNEL_MATERN12 3 /* exp(-r)                                 */
 
 /* ---- arithmetic of the large GEMMs of the factorisation layer (per call) ----------------------
- * FP64 matrix products with M, N and K all >= min_dim can be computed on the tcgen05 INT8 tensor
- * path instead of the FP64 DMMA units (B200 has no FP64 kind on tcgen05):
+ * FP64 matrix products with M, N and K all >= min_dim and M*N*K >= min_mnk can be computed on the tcgen05 INT8
+ * tensor path instead of the FP64 DMMA units (B200 has no FP64 kind on tcgen05):
  *   PLMC_GEMM_INT8_DIGITS  operands split into `precision` (1..7) signed 8-bit digit planes, 8p-1 bits
  *                          relative to the row/column maximum, p(p+1)/2 INT8 products (csrc/ozaki.cu);
  *   PLMC_GEMM_INT8_RNS     operands scaled to integers and reduced modulo `precision` (8..18) pairwise
@@ -68,6 +68,10 @@ typedef struct plmc_gemm_cfg {
     int alt_precision;
     int rns_min_k;
     long long rns_min_mnk;
+    /* products with M*N*K below min_mnk stay on the FP64 kernel whatever their dimensions (0: no work floor):
+     * with min_dim = 128 this sends the tall-skinny leaf applications of the triangular solves (m x 128 x 128,
+     * m large) to the tensor path and keeps the tiny ones off it. */
+    long long min_mnk;
 } plmc_gemm_cfg;
 
 int plmc_version(void);

@@ -26,7 +26,7 @@ class GemmCfg(ctypes.Structure):
     """plmc_gemm_cfg (include/plmc_b200.h): per-call arithmetic of the large GEMMs of the factorisation layer."""
     _fields_ = [("ws", c_void_p), ("ws_bytes", c_longlong), ("mode", c_int), ("precision", c_int),
                 ("min_dim", c_int), ("flags", c_int), ("alt_precision", c_int), ("rns_min_k", c_int),
-                ("rns_min_mnk", c_longlong)]
+                ("rns_min_mnk", c_longlong), ("min_mnk", c_longlong)]
 
 
 CFG = ctypes.POINTER(GemmCfg)

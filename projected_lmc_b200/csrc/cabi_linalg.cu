@@ -50,6 +50,7 @@ static bool make_ctx(LaCtx& cx, cudaStream_t st, int batch, const plmc_gemm_cfg*
     cx.oz_mode = cfg->mode;
     cx.oz_prec = cfg->precision;
     cx.oz_min = cfg->min_dim;
+    cx.oz_min_mnk = cfg->min_mnk;
     cx.oz_flags = cfg->flags;
     if (cfg->mode == PLMC_GEMM_INT8_RNS) {
         cx.oz_alt = cfg->alt_precision;

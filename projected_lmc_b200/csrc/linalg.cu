@@ -91,7 +91,8 @@ void trace_report() {
 static void gemm_impl(LaCtx& cx, bool aKC, bool bKC, BMat A, BMat B, BMat C, int M, int N, int K, double alpha,
                       double beta, int lower, int triA, int triB, int* path) {
     if (cx.status) return;
-    if (cx.oz_mode > 0 && cx.oz_prec > 0 && !triA && !triB && M >= cx.oz_min && N >= cx.oz_min && K >= cx.oz_min) {
+    if (cx.oz_mode > 0 && cx.oz_prec > 0 && !triA && !triB && M >= cx.oz_min && N >= cx.oz_min && K >= cx.oz_min &&
+        (long long)M * N * K >= cx.oz_min_mnk) {
         // large update: FP64 product through the INT8 tensor path (all batch members per launch when
         // the plane scratch holds them, otherwise in passes; everything is ordered on the one stream)
         const bool same = (A.p == B.p && A.ld == B.ld && aKC == bKC && M == N);

@@ -31,6 +31,7 @@ struct LaCtx {
     int oz_mode = 0;
     int oz_prec = 0;
     int oz_min = 1024;  // smallest M, N, K routed to the INT8 path
+    long long oz_min_mnk = 0;   // and the least work M*N*K
     int oz_flags = 0;   // bit 0: single-CTA kernel in mode 2
     // mode 2: digit planes (oz_alt slices) for products with K < oz_rns_min_k or M N K < oz_rns_min_mnk
     int oz_alt = 0;

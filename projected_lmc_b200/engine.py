@@ -77,7 +77,11 @@ class LatentEngine:
     # that the whole test-suite can be run in any mode.
     gemm_mode = __import__("os").environ.get("PLMC_GEMM_MODE", "rns")
     fp64_slices = int(__import__("os").environ.get("PLMC_FP64_SLICES", "7"))
-    fp64_min_dim = int(__import__("os").environ.get("PLMC_FP64_MIN_DIM", "512"))
+    fp64_min_dim = int(__import__("os").environ.get("PLMC_FP64_MIN_DIM", "128"))
+    # ... and the least work M*N*K (default 512^3: with min_dim 128 the tall-skinny m x 128 x 128 leaf applications
+    # of the triangular solves take the tensor path from m = 8192 on, the small products stay on DMMA)
+    fp64_min_mnk = int(float(__import__("os").environ.get("PLMC_FP64_MIN_MNK", str(512 ** 3))))
+    fp64_min_order = 1024    # matrices below this order are factorised in pure FP64
     rns_moduli = int(__import__("os").environ.get("PLMC_RNS_MODULI", "16"))
     # precision of the explicit inverse of the training iteration (K^-1 = L^-T L^-1: trtri + lauum).  K^-1 feeds
     # ONLY the gradient sweep tr((alpha alpha^T - K^-1) dK): the loss, alpha and the log-determinant come from L,
@@ -99,12 +103,12 @@ class LatentEngine:
 
     def _configure_fp64(self, device, np_, q=1):
         mode, md = self.emulation_mode(), self.fp64_min_dim
-        key = (mode, md, self.fp64_slices, self.fp64_slices_kinv, self.rns_moduli, self.rns_moduli_kinv,
+        key = (mode, md, self.fp64_min_mnk, self.fp64_slices, self.fp64_slices_kinv, self.rns_moduli, self.rns_moduli_kinv,
                self.rns_flags, self.rns_min_k, self.rns_min_mnk, str(device), np_, q)
         if key == self._cfg_key:
             return
         self._cfg_key = key
-        if mode == "fp64" or np_ < 2 * md:
+        if mode == "fp64" or np_ < max(self.fp64_min_order, 2 * md):
             self._cfg = (None, None)
             return
         h = np_ // 2
@@ -132,13 +136,13 @@ class LatentEngine:
             alt = self.fp64_slices if (self.rns_min_k > 0 or self.rns_min_mnk > 0) else 0
             altk = min(self.fp64_slices_kinv or alt, alt)
             self._cfg = (ops.gemm_cfg(self._oz, ops.GEMM_INT8_RNS, self.rns_moduli, md, self.rns_flags, alt,
-                                      self.rns_min_k, self.rns_min_mnk),
+                                      self.rns_min_k, self.rns_min_mnk, self.fp64_min_mnk),
                          ops.gemm_cfg(self._oz, ops.GEMM_INT8_RNS, mk, md, self.rns_flags, altk,
-                                      self.rns_min_k, self.rns_min_mnk))
+                                      self.rns_min_k, self.rns_min_mnk, self.fp64_min_mnk))
         else:
             sk = min(self.fp64_slices_kinv or self.fp64_slices, self.fp64_slices)
-            self._cfg = (ops.gemm_cfg(self._oz, ops.GEMM_INT8_DIGITS, self.fp64_slices, md),
-                         ops.gemm_cfg(self._oz, ops.GEMM_INT8_DIGITS, sk, md))
+            self._cfg = (ops.gemm_cfg(self._oz, ops.GEMM_INT8_DIGITS, self.fp64_slices, md, min_mnk=self.fp64_min_mnk),
+                         ops.gemm_cfg(self._oz, ops.GEMM_INT8_DIGITS, sk, md, min_mnk=self.fp64_min_mnk))
 
     @property
     def cfg_main(self):

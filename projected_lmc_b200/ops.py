@@ -44,12 +44,12 @@ def _on_device(fn):
 
 
 def gemm_cfg(ws, mode: int, precision: int, min_dim: int = 512, flags: int = 0, alt_precision: int = 0,
-             rns_min_k: int = 0, rns_min_mnk: int = 0):
+             rns_min_k: int = 0, rns_min_mnk: int = 0, min_mnk: int = 0):
     """plmc_gemm_cfg for the factorisation calls (None = pure FP64).  The struct keeps its scratch tensor alive."""
     if ws is None or mode == GEMM_FP64 or precision <= 0:
         return None
     cfg = GemmCfg(ptr(ws), ws.numel() * ws.element_size(), int(mode), int(precision), max(128, int(min_dim)),
-                  int(flags), int(alt_precision), int(rns_min_k), int(rns_min_mnk))
+                  int(flags), int(alt_precision), int(rns_min_k), int(rns_min_mnk), int(min_mnk))
     cfg._keepalive = ws
     return cfg
 

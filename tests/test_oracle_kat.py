@@ -1,4 +1,5 @@
 """Known-answer tests of the oracle (CPU): dependency-free identities, see oracle/kat.py."""
+import math
 import warnings
 
 import pytest
@@ -80,3 +81,67 @@ def test_psd_safe_cholesky_jitter_only_on_failing_members():
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             O.psd_safe_cholesky(bad[None], max_tries=3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Independent third-party pins of the gpytorch layer the oracle restates (kernel values and the Gaussian
+# log-density): scikit-learn's ARD RBF / Matern(nu) kernels and scipy's multivariate normal.  Neither shares code
+# with the oracle or with the shim the reference-run fixtures were generated over.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel,nu", [("rbf", None), ("matern52", 2.5), ("matern32", 1.5), ("matern12", 0.5)])
+def test_base_kernel_matches_scikit_learn(kernel, nu):
+    from sklearn.gaussian_process.kernels import RBF, Matern
+
+    g = torch.Generator().manual_seed(5)
+    X1 = torch.rand(37, 4, generator=g) * 2 - 1
+    X2 = torch.rand(23, 4, generator=g) * 2 - 1
+    ell = torch.rand(3, 4, generator=g) + 0.3
+    K = O.base_kernel(kernel, X1, X2, ell[:, None, :], zero_diag=False)
+    Ktrain = O.base_kernel(kernel, X1, X1, ell[:, None, :], zero_diag=True)
+    for l in range(3):
+        ls = ell[l].numpy()
+        sk = RBF(length_scale=ls) if nu is None else Matern(length_scale=ls, nu=nu)
+        # the expansion-based squared distance (|a|^2 + |b|^2 - 2ab) carries ~1e-15 absolute round-off; the nu = 1/2
+        # kernel exp(-sqrt(s)) turns that into ~3e-8 next to coincident points, everywhere else it stays ~1e-15
+        tol = 1e-12
+        assert abs(K[l].numpy() - sk(X1.numpy(), X2.numpy())).max() < tol
+        ref = sk(X1.numpy())
+        tol_train = 1e-7 if kernel == "matern12" else 1e-12
+        assert abs(Ktrain[l].numpy() - ref).max() < tol_train
+
+
+def test_mvn_log_prob_matches_scipy():
+    from scipy.stats import multivariate_normal
+
+    g = torch.Generator().manual_seed(6)
+    n = 60
+    X = torch.rand(n, 3, generator=g) * 2 - 1
+    ell = torch.rand(2, 3, generator=g) + 0.5
+    noise = torch.tensor([0.05, 0.3])
+    K = O.base_kernel("matern52", X, X, ell[:, None, :], zero_diag=True) + torch.diag_embed(noise[:, None].expand(-1, n))
+    y = torch.randn(2, n, generator=g)
+    lp = O.mvn_log_prob(K, y)
+    for l in range(2):
+        ref = multivariate_normal(mean=None, cov=K[l].numpy(), allow_singular=False).logpdf(y[l].numpy())
+        assert abs(lp[l].item() - ref) <= 1e-10 * abs(ref)
+
+
+def test_psd_safe_cholesky_jitter_schedule_matches_the_published_one():
+    """linear_operator 0.5.0 psd_safe_cholesky: jitter 1e-8 * 10^i (float64) on failing members only, NotPSD after
+    max_tries; the factor of a member that did not fail is the plain Cholesky factor."""
+    g = torch.Generator().manual_seed(7)
+    A = torch.randn(2, 12, 5, generator=g)
+    K = A @ A.transpose(1, 2)                       # rank 5 of 12: singular
+    K[1] = K[1] + 0.5 * torch.eye(12)               # member 1 is fine
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        L = O.psd_safe_cholesky(K, max_tries=6)
+    assert torch.allclose(L[1], torch.linalg.cholesky(K[1]), rtol=0, atol=0)
+    assert len(w) >= 1
+    rec = L[0] @ L[0].T - K[0]
+    off = rec - torch.diag(torch.diagonal(rec))
+    assert off.abs().max() < 1e-12
+    jit = torch.diagonal(rec)
+    assert torch.allclose(jit, jit[0].expand_as(jit), rtol=1e-6, atol=1e-16)
+    ratio = math.log10(jit[0].item() / 1e-8)
+    assert abs(ratio - round(ratio)) < 1e-3 and 0 <= round(ratio) <= 5

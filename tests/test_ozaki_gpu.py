@@ -121,10 +121,12 @@ def test_accuracy_scales_with_slices(slices, tol):
 
 @pytest.fixture(params=["digits", "rns"])
 def force_emulation_everywhere(request):
-    old = LatentEngine.fp64_slices, LatentEngine.fp64_min_dim, LatentEngine.gemm_mode
-    LatentEngine.fp64_slices, LatentEngine.fp64_min_dim, LatentEngine.gemm_mode = 7, 128, request.param
+    E = LatentEngine
+    old = (E.fp64_slices, E.fp64_min_dim, E.gemm_mode, E.fp64_min_mnk, E.fp64_min_order, E.rns_min_k, E.rns_min_mnk)
+    E.fp64_slices, E.fp64_min_dim, E.gemm_mode, E.fp64_min_mnk, E.fp64_min_order = 7, 128, request.param, 0, 256
+    E.rns_min_k, E.rns_min_mnk = 0, 0            # "rns" really means residues for every product
     yield
-    LatentEngine.fp64_slices, LatentEngine.fp64_min_dim, LatentEngine.gemm_mode = old
+    (E.fp64_slices, E.fp64_min_dim, E.gemm_mode, E.fp64_min_mnk, E.fp64_min_order, E.rns_min_k, E.rns_min_mnk) = old
 
 
 @pytest.mark.parametrize("variant,kernel", [("PLMC", "matern52"), ("PLMC_fast", "rbf")])
