@@ -112,14 +112,30 @@ int plmc_col_mean(const double* X, long long n, int d, double* xmean, void* stre
 int plmc_scale_inputs(const double* X, const double* xmean, const double* ell, double* Z, double* zn, long long n,
                       int d, int dpad, long long rows_pad, int q, void* stream);
 /* K[l] (lower 128-tiles of a [npad, ld] matrix) = os[l]*k(s_ij) + diag_add[l]*I,
- * identity in the padding.  os may be NULL (no ScaleKernel).                    */
+ * identity in the padding.  os may be NULL (no ScaleKernel).  accumulate != 0: K[l] += os[l]*k(s_ij)
+ * (a further component of an additive kernel, handle_covar_ `decomp`, projected_lmc.py:151-167; the
+ * diagonal term and the padding belong to the first component).                                    */
 int plmc_gram(const double* Z, const double* zn, int kernel_id, const double* os, const double* diag_add, double* K,
-              long long ld, long long stride, long long n, long long npad, int dpad, int q, void* stream);
+              long long ld, long long stride, long long n, long long npad, int dpad, int q, int accumulate,
+              void* stream);
 /* Kx[l, i, j] = os[l]*k(train_i, test_j): [q, npad, ldx] with ldx >= mt, mt%128==0;
  * rows >= n are zero.                                                            */
 int plmc_cross_gram(const double* Ztrain, const double* zntrain, const double* Ztest, const double* zntest,
                     int kernel_id, const double* os, double* Kx, long long ldx, long long stride, long long n,
-                    long long npad, long long mt_rows_pad, long long mt, int dpad, int q, void* stream);
+                    long long npad, long long mt_rows_pad, long long mt, int dpad, int q, int accumulate,
+                    void* stream);
+
+/* ---- adjoint of the cross-Gram block (inducing-point / SGPR variant: ExactGPModel(n_inducing_points=m),
+ * projected_lmc.py:302-303 -> gpytorch InducingPointKernel).  Zr [q, rows_pad_r, dpad] / Zc [q, rows_pad_c, dpad]
+ * are the scaled row (inducing) and column (data) points as produced by plmc_scale_inputs, G [q, nr, ldg] the
+ * cotangent of K[l,i,j] = os[l] k(|zr_i - zc_j|^2).  Outputs: g_ell [q, d], g_os [q] (may be NULL),
+ * g_rows [nr, d] = gradient w.r.t. the UNscaled row points summed over the latents.  partial: workspace of
+ * plmc_cross_gram_bwd_ws(nr, nc, d, q) bytes.  Deterministic (fixed-order reductions, no atomics).          */
+long long plmc_cross_gram_bwd_ws(long long nr, long long nc, int d, int q);
+int plmc_cross_gram_bwd(const double* Zr, long long rows_pad_r, const double* Zc, long long rows_pad_c, const double* G,
+                        long long ldg, long long strideG, int kernel_id, const double* os, const double* ell,
+                        double* g_ell, double* g_os, double* g_rows, double* partial, long long nr, long long nc, int d,
+                        int dpad, int q, void* stream);
 
 /* ---- (3) factorisation: MultivariateNormal.log_prob -> psd_safe_cholesky,
  * triangular solve, logdet (gpytorch; reached from projected_lmc.py:1201).     */

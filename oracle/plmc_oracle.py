@@ -60,14 +60,46 @@ class OracleParams:
     diagonal_B: bool = False
     eps: float = 1e-3                          # :900, :993
     extra: dict = field(default_factory=dict)
+    # additive `decomp` kernel (handle_covar_, :131-181): one entry per sub-kernel; None = the single ARD kernel above
+    components: Optional[list] = None
+    # ExactGPModel(n_inducing_points=m) (:302-303): gpytorch InducingPointKernel, inducing points [m, d] shared by
+    # the latents; None = exact GP
+    inducing_points: Optional[torch.Tensor] = None
 
     @property
     def q(self) -> int:
         return self.raw_lengthscale.shape[0]
 
 
+@dataclass
+class OracleComponent:
+    """One sub-kernel of handle_covar_'s additive kernel (projected_lmc.py:151-167): an ARD kernel on the input
+    dimensions ``dims`` wrapped in a ScaleKernel, with an optional lengthscale prior (:135-149)."""
+
+    dims: list
+    raw_lengthscale: torch.Tensor              # [q, 1, len(dims)]
+    raw_outputscale: Optional[torch.Tensor]    # [q] (always present when there is more than one component)
+    prior_loc: Optional[torch.Tensor] = None   # prior mean of the lengthscales (len(dims) values)
+    prior_width: Optional[torch.Tensor] = None  # deviation-to-mean ratio
+
+
 def softplus(x: torch.Tensor) -> torch.Tensor:
     return F.softplus(x)
+
+
+def lengthscale_log_prior(c: OracleComponent) -> torch.Tensor:
+    """log-density of softplus(raw_lengthscale) under the prior handle_covar_ builds (:141-149):
+    one dimension -> Normal(loc, loc*width); several -> MultivariateNormal(loc, diag(loc*width)) -- the
+    covariance, not the standard deviation, is loc*width there.  Summed over latents."""
+    ell = softplus(c.raw_lengthscale)                                   # [q, 1, d_g]
+    loc, width = c.prior_loc, c.prior_width
+    if len(c.dims) > 1:
+        var = loc * width
+        lp = -0.5 * ((ell - loc) ** 2 / var).sum(-1) - 0.5 * torch.log(var).sum() - 0.5 * len(c.dims) * math.log(2 * math.pi)
+    else:
+        sd = loc * width
+        lp = -((ell - loc) ** 2) / (2 * sd**2) - torch.log(sd) - 0.5 * math.log(2 * math.pi)
+    return lp.sum()
 
 
 def lengthscale(p: OracleParams) -> torch.Tensor:
@@ -132,6 +164,17 @@ def gram(p: OracleParams, x1: torch.Tensor, x2: Optional[torch.Tensor] = None, t
     """covar_module(x) of ExactGPModel.forward, projected_lmc.py:1088-1091 (ScaleKernel when outputscales)."""
     same = x2 is None
     x2 = x1 if same else x2
+    if p.components is not None:
+        # AdditiveKernel of ScaleKernels, each on its own active dimensions (gpytorch slices x[..., active_dims]
+        # before the kernel, so the centring of sq_dist is over the selected columns)
+        K = 0.0
+        for c in p.components:
+            Kg = base_kernel(p.kernel, x1[:, c.dims], x2[:, c.dims], softplus(c.raw_lengthscale),
+                             zero_diag=(same and not training))
+            if c.raw_outputscale is not None:
+                Kg = Kg * softplus(c.raw_outputscale)[:, None, None]
+            K = K + Kg
+        return K
     K = base_kernel(p.kernel, x1, x2, lengthscale(p), zero_diag=(same and not training))
     os_ = outputscale(p)
     if os_ is not None:
@@ -218,8 +261,36 @@ def project_data(p: OracleParams, Y: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # the loss  (ProjectedLMCmll.forward, projected_lmc.py:1178-1241)
 # ---------------------------------------------------------------------------
+def prior_variance(p: OracleParams, dtype=DTYPE) -> torch.Tensor:
+    """k(x, x) of the stationary kernel: the sum of the outputscales (1 without a ScaleKernel).  [q]"""
+    if p.components is not None:
+        return sum((torch.ones(p.q, dtype=dtype) if c.raw_outputscale is None else softplus(c.raw_outputscale))
+                   for c in p.components)
+    os_ = outputscale(p)
+    return torch.ones(p.q, dtype=dtype) if os_ is None else os_
+
+
+def sgpr_low_rank(p: OracleParams, x1: torch.Tensor, x2: torch.Tensor, max_tries: int = 3) -> torch.Tensor:
+    """gpytorch 1.11 InducingPointKernel._get_covariance without the diagonal correction:
+    Q(x1, x2) = K_1u K_uu^-1 K_u2, K_uu factorised by psd_safe_cholesky.  Dense [q, n1, n2]."""
+    U = p.inducing_points
+    Luu = psd_safe_cholesky(gram(p, U, training=True), max_tries)
+    A1 = torch.linalg.solve_triangular(Luu, gram(p, U, x1, training=True), upper=False)
+    A2 = A1 if x2 is x1 else torch.linalg.solve_triangular(Luu, gram(p, U, x2, training=True), upper=False)
+    return A1.transpose(-1, -2) @ A2
+
+
 def latent_log_probs(p: OracleParams, X: torch.Tensor, TY: torch.Tensor, max_tries: int = 3) -> torch.Tensor:
     """likelihood(dist).log_prob(TY), projected_lmc.py:1200-1201 -> [q]."""
+    n = X.shape[0]
+    if p.inducing_points is not None:
+        # training-mode InducingPointKernel: covariance Q_ff (no diagonal correction) + noise, and the added loss
+        # term -1/2 sum_i (k_ii - q_ii) / noise that ExactMarginalLogLikelihood._add_other_terms adds per latent
+        Q = sgpr_low_rank(p, X, X, max_tries)
+        s2 = noise(p)
+        lp = mvn_log_prob(Q + torch.diag_embed(s2[:, None].expand(-1, n)), TY, max_tries)
+        diag = prior_variance(p, X.dtype)[:, None] - torch.diagonal(Q, dim1=-2, dim2=-1)
+        return lp - 0.5 * (diag / s2[:, None]).sum(-1)
     K = gram(p, X, training=True)
     n = X.shape[0]
     K = K + torch.diag_embed(noise(p)[:, None].expand(-1, n))
@@ -262,7 +333,13 @@ def mll(p: OracleParams, X: torch.Tensor, Y: torch.Tensor, max_tries: int = 3) -
     """ProjectedLMCmll.forward, projected_lmc.py:1178-1241 (scalar, per data point)."""
     n, ptasks = Y.shape
     TY = project_data(p, Y)
-    latent = latent_log_probs(p, X, TY, max_tries).sum() / n
+    lat = latent_log_probs(p, X, TY, max_tries)
+    # ExactMarginalLogLikelihood._add_other_terms (:1202): every prior's summed log-density is added to the whole
+    # [q] vector (gpytorch 1.11), so it counts q times after the sum below
+    for c in (p.components or []):
+        if c.prior_loc is not None:
+            lat = lat + lengthscale_log_prior(c)
+    latent = lat.sum() / n
     t0, t1, t2 = projection_terms(p, Y)
     return latent + (t0 + t1 + t2) - 0.5 * (ptasks - p.q) * math.log(2 * math.pi)
 
@@ -329,14 +406,37 @@ def predict(p: OracleParams, X: torch.Tensor, Y: torch.Tensor, Xs: torch.Tensor,
     """
     n = X.shape[0]
     TY = project_data(p, Y)
+    if p.inducing_points is not None:
+        # eval-mode InducingPointKernel (sgpr_diagonal_correction on): the joint covariance on [X; X*] is
+        # Q + diag(clamp(k_ii - q_ii, 0)); exact-GP prediction under it
+        kss_ = prior_variance(p, X.dtype)[:, None]
+        Qff = sgpr_low_rank(p, X, X, max_tries)
+        corr = (kss_ - torch.diagonal(Qff, dim1=-2, dim2=-1)).clamp_min(0)
+        K = Qff + torch.diag_embed(corr + noise(p)[:, None])
+        Ks = sgpr_low_rank(p, X, Xs, max_tries)
+        qss = torch.diagonal(sgpr_low_rank(p, Xs, Xs, max_tries), dim1=-2, dim2=-1)
+        L = psd_safe_cholesky(K, max_tries)
+        alpha = torch.cholesky_solve(TY.unsqueeze(-1), L).squeeze(-1)
+        lat_mean = (Ks * alpha[:, :, None]).sum(1)
+        V = torch.linalg.solve_triangular(L, Ks, upper=False)
+        lat_var = qss + (kss_ - qss).clamp_min(0) - V.pow(2).sum(1)
+        Ht = lmc_coefficients(p)
+        mean = lat_mean.T @ Ht
+        var_f = lat_var.T @ Ht.pow(2) + p.eps
+        Fch = task_noise_factor(p)
+        return mean, var_f, var_f + (Fch @ Fch.T).diagonal()[None, :]
     K = gram(p, X, training=False) + torch.diag_embed(noise(p)[:, None].expand(-1, n))
     L = psd_safe_cholesky(K, max_tries)
     alpha = torch.cholesky_solve(TY.unsqueeze(-1), L).squeeze(-1)          # mean_cache
     Ks = gram(p, X, Xs, training=False)                                     # [q, n, n*]
     lat_mean = (Ks * alpha[:, :, None]).sum(1)                              # [q, n*]
     V = torch.linalg.solve_triangular(L, Ks, upper=False)
-    os_ = outputscale(p)
-    kss = torch.ones(p.q, 1, dtype=X.dtype) if os_ is None else os_[:, None]
+    if p.components is not None:
+        kss = sum((torch.ones(p.q, dtype=X.dtype) if c.raw_outputscale is None else softplus(c.raw_outputscale))
+                  for c in p.components)[:, None]
+    else:
+        os_ = outputscale(p)
+        kss = torch.ones(p.q, 1, dtype=X.dtype) if os_ is None else os_[:, None]
     lat_var = kss - V.pow(2).sum(1)                                         # [q, n*]
     Ht = lmc_coefficients(p)                                                # [q, p]
     mean = lat_mean.T @ Ht

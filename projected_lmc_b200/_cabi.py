@@ -47,8 +47,10 @@ _SIGNATURES = {
     "plmc_project_bwd": [P, P, LL, P, P, LL, I, I, P],
     "plmc_col_mean": [P, LL, I, P, P],
     "plmc_scale_inputs": [P, P, P, P, P, LL, I, I, LL, I, P],
-    "plmc_gram": [P, P, I, P, P, P, LL, LL, LL, LL, I, I, P],
-    "plmc_cross_gram": [P, P, P, P, I, P, P, LL, LL, LL, LL, LL, LL, I, I, P],
+    "plmc_gram": [P, P, I, P, P, P, LL, LL, LL, LL, I, I, I, P],
+    "plmc_cross_gram": [P, P, P, P, I, P, P, LL, LL, LL, LL, LL, LL, I, I, I, P],
+    "plmc_cross_gram_bwd_ws": [LL, LL, I, I],
+    "plmc_cross_gram_bwd": [P, LL, P, LL, P, LL, LL, I, P, P, P, P, P, P, LL, LL, I, I, I, P],
     "plmc_potrf_batched": [P, LL, LL, LL, I, P, P, CFG, P],
     "plmc_trsm_batched": [I, P, LL, LL, LL, I, P, P, LL, LL, LL, D, CFG, P],
     "plmc_solve_logdet": [P, LL, LL, LL, LL, I, P, P, LL, P, P, P, LL, P, P, P],
@@ -74,7 +76,7 @@ _SIGNATURES = {
     "plmc_peak_mixed": [I, I, LL, LL, P, P],
 }
 _RET_LL = {"plmc_npad", "plmc_dinv_bytes", "plmc_project_bwd_ws", "plmc_grad_ws", "plmc_ozaki_ws_bytes",
-           "plmc_rns_ws_bytes"}
+           "plmc_rns_ws_bytes", "plmc_cross_gram_bwd_ws"}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -12,7 +12,7 @@
 // the epilogue: K is written exactly once (lower 128-tiles only).
 //
 // Algorithmic bytes: 8*q*n(n+1)/2 written (Gram), the same read (sweep).
-#include "plmc_common.cuh"
+#include "kernel_math.cuh"
 
 namespace plmc {
 
@@ -20,46 +20,6 @@ constexpr int GR_THREADS = 256;
 constexpr int GR_KC = 32;  // input-dimension chunk staged in shared memory by the Gram kernel
 
 __host__ __device__ inline int gram_lds(int dpad) { return ((dpad + 11) / 16) * 16 + 4; }
-
-template <int KID>
-__device__ __forceinline__ double kernel_value(double s) {
-    if (KID == 0) return exp(-0.5 * s);
-    const double r = sqrt(fmax(s, 1e-30));
-    if (KID == 1) {
-        const double a = 2.23606797749978969641 * r;  // sqrt(5) r
-        return (1.0 + a + (5.0 / 3.0) * r * r) * exp(-a);
-    }
-    if (KID == 2) {
-        const double a = 1.73205080756887729353 * r;
-        return (1.0 + a) * exp(-a);
-    }
-    return exp(-r);
-}
-
-// k(s) and dk/ds
-template <int KID>
-__device__ __forceinline__ void kernel_value_grad(double s, double& k, double& dk) {
-    if (KID == 0) {
-        k = exp(-0.5 * s);
-        dk = -0.5 * k;
-        return;
-    }
-    const double r = sqrt(fmax(s, 1e-30));
-    if (KID == 1) {
-        const double a = 2.23606797749978969641 * r;
-        const double e = exp(-a);
-        k = (1.0 + a + (5.0 / 3.0) * r * r) * e;
-        dk = -(5.0 / 6.0) * (1.0 + a) * e;
-    } else if (KID == 2) {
-        const double a = 1.73205080756887729353 * r;
-        const double e = exp(-a);
-        k = (1.0 + a) * e;
-        dk = -1.5 * e;
-    } else {
-        k = exp(-r);
-        dk = (s > 1e-30) ? -0.5 * k / r : 0.0;
-    }
-}
 
 // xmean[k] = mean_i X[i, k]
 __global__ void __launch_bounds__(256) col_mean_kernel(const double* __restrict__ X, long long n, int d,
@@ -98,7 +58,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1)
     gram_kernel(const double* __restrict__ Zr, const double* __restrict__ znr, long long rows_pad_r,
                 const double* __restrict__ Zc, const double* __restrict__ znc, long long rows_pad_c,
                 const double* __restrict__ os, const double* __restrict__ diag_add, double* __restrict__ Kout,
-                long long ld, long long stride, long long n, int dpad, int tiles_c) {
+                long long ld, long long stride, long long n, int dpad, int tiles_c, int accumulate) {
     extern __shared__ __align__(16) double sm[];
     const int lds = gram_lds(dpad < GR_KC ? dpad : GR_KC);
     double* Zi = sm;
@@ -187,6 +147,10 @@ __global__ void __launch_bounds__(GR_THREADS, 1)
         const long long gi = i0 + wm * 64 + i * 8 + g;
         const long long gj = j0 + wn * 32 + j * 8 + 2 * t;
         double v[2];
+        // accumulate: a further component of an additive kernel (sum_g os_g k_g) is added onto the tile; the
+        // noise diagonal and the identity padding were written with the first component
+        double2 old = make_double2(0.0, 0.0);
+        if (accumulate) old = *reinterpret_cast<const double2*>(Kl + gi * ld + gj);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const long long gje = gj + e;
@@ -194,14 +158,14 @@ __global__ void __launch_bounds__(GR_THREADS, 1)
             if (MODE == 0) {
                 if (gi == gje) s = 0.0;
                 double kv = osl * kernel_value<KID>(s);
-                if (gi == gje) kv += dadd;
-                if (gi >= n || gje >= n) kv = (gi == gje) ? 1.0 : 0.0;
+                if (gi == gje && !accumulate) kv += dadd;
+                if (gi >= n || gje >= n) kv = (gi == gje && !accumulate) ? 1.0 : 0.0;
                 v[e] = kv;
             } else {
                 v[e] = (gi < n) ? osl * kernel_value<KID>(s) : 0.0;
             }
         }
-        *reinterpret_cast<double2*>(Kl + gi * ld + gj) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(Kl + gi * ld + gj) = make_double2(v[0] + old.x, v[1] + old.y);
     }
 }
 
@@ -387,13 +351,13 @@ template <int MODE>
 static int launch_gram(int kernel_id, dim3 grid, size_t smem, cudaStream_t st, const double* Zr, const double* znr,
                        long long rpr, const double* Zc, const double* znc, long long rpc, const double* os,
                        const double* diag_add, double* K, long long ld, long long stride, long long n, int dpad,
-                       int tiles_c) {
+                       int tiles_c, int accumulate) {
 #define PLMC_GRAM_CASE(KID)                                                                                     \
     case KID:                                                                                                   \
         if (smem > 48 * 1024)                                                                                   \
             cudaFuncSetAttribute(gram_kernel<KID, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         gram_kernel<KID, MODE><<<grid, GR_THREADS, smem, st>>>(Zr, znr, rpr, Zc, znc, rpc, os, diag_add, K, ld,  \
-                                                               stride, n, dpad, tiles_c);                       \
+                                                               stride, n, dpad, tiles_c, accumulate);           \
         break;
     switch (kernel_id) {
         PLMC_GRAM_CASE(0)
@@ -430,7 +394,8 @@ int plmc_scale_inputs(const double* X, const double* xmean, const double* ell, d
 }
 
 int plmc_gram(const double* Z, const double* zn, int kernel_id, const double* os, const double* diag_add, double* K,
-              long long ld, long long stride, long long n, long long npad, int dpad, int q, void* stream) {
+              long long ld, long long stride, long long n, long long npad, int dpad, int q, int accumulate,
+              void* stream) {
     if (!Z || !zn || !diag_add || !K || n <= 0 || npad < n || (npad % 128) || ld < npad || (ld & 1) || dpad <= 0 ||
         (dpad & 3) || q <= 0 || q > 65535)
         return PLMC_ERR_BADARG;
@@ -440,12 +405,13 @@ int plmc_gram(const double* Z, const double* zn, int kernel_id, const double* os
     const size_t smem = (size_t)(2 * 128 * gram_lds(dpad < GR_KC ? dpad : GR_KC) + 256 + 64 * GR_THREADS) * 8;
     if (smem > 227 * 1024) return PLMC_ERR_BADARG;
     return launch_gram<0>(kernel_id, dim3((unsigned)tiles, 1, q), smem, (cudaStream_t)stream, Z, zn, npad, Z, zn, npad,
-                          os, diag_add, K, ld, stride, n, dpad, (int)tm);
+                          os, diag_add, K, ld, stride, n, dpad, (int)tm, accumulate);
 }
 
 int plmc_cross_gram(const double* Ztrain, const double* zntrain, const double* Ztest, const double* zntest,
                     int kernel_id, const double* os, double* Kx, long long ldx, long long stride, long long n,
-                    long long npad, long long mt_rows_pad, long long mt, int dpad, int q, void* stream) {
+                    long long npad, long long mt_rows_pad, long long mt, int dpad, int q, int accumulate,
+                    void* stream) {
     if (!Ztrain || !zntrain || !Ztest || !zntest || !Kx || n <= 0 || npad < n || (npad % 128) || mt <= 0 ||
         (mt % 128) || mt_rows_pad < mt || ldx < mt || (ldx & 1) || dpad <= 0 || (dpad & 3) || q <= 0 || q > 65535)
         return PLMC_ERR_BADARG;
@@ -454,7 +420,7 @@ int plmc_cross_gram(const double* Ztrain, const double* zntrain, const double* Z
     const size_t smem = (size_t)(2 * 128 * gram_lds(dpad < GR_KC ? dpad : GR_KC) + 256 + 64 * GR_THREADS) * 8;
     if (smem > 227 * 1024) return PLMC_ERR_BADARG;
     return launch_gram<1>(kernel_id, dim3((unsigned)(tr * tc), 1, q), smem, (cudaStream_t)stream, Ztrain, zntrain,
-                          npad, Ztest, zntest, mt_rows_pad, os, nullptr, Kx, ldx, stride, n, dpad, (int)tc);
+                          npad, Ztest, zntest, mt_rows_pad, os, nullptr, Kx, ldx, stride, n, dpad, (int)tc, accumulate);
 }
 
 long long plmc_grad_ws(long long npad, int d, int q) {

@@ -47,6 +47,7 @@ class LatentEngine:
         self._cfg = (None, None)
         self._cfg_key = None
         self._pinned = None
+        self._xsub = {}
         self.last_jitter = None
         self.generation = 0     # bumped whenever ws['K'] is rewritten (prediction caches compare it)
 
@@ -162,24 +163,57 @@ class LatentEngine:
         if self._xmean_key != key:
             self._xmean = ops.col_mean(X)
             self._xmean_key = key
+            self._xsub = {}
         return self._xmean
+
+    def _sub_inputs(self, X, dims):
+        """(X[:, dims] contiguous, its column means) for one component of an additive kernel (cached with X)."""
+        full = self.xmean(X)
+        if tuple(dims) == tuple(range(X.shape[1])):
+            return X, full
+        hit = self._xsub.get(tuple(dims))
+        if hit is None:
+            idx = torch.as_tensor(list(dims), device=X.device)
+            Xg = X.index_select(1, idx).contiguous()
+            hit = (Xg, ops.col_mean(Xg))
+            self._xsub[tuple(dims)] = hit
+        return hit
+
+    def _scaled(self, X, comps, rows_pad):
+        """Per component: (Z [q, rows_pad, dpad_g], zn, X_g, xmean_g)."""
+        out = []
+        for kid, dims, ell, os_ in comps:
+            Xg, xm = self._sub_inputs(X, dims)
+            Z, zn = ops.scale_inputs(Xg, xm, ell, rows_pad)
+            out.append((Z, zn, Xg, xm))
+        return out
+
+    @staticmethod
+    def _gram_all(comps, scaled, diag_add, K, n, sl=None):
+        """K = sum_g os_g k_g + diag_add I (lower tiles, identity padding); sl restricts to a slice of latents."""
+        for g, ((kid, dims, ell, os_), (Z, zn, _, _)) in enumerate(zip(comps, scaled)):
+            if sl is not None:
+                Z, zn, os_ = Z[sl], zn[sl], (None if os_ is None else os_[sl])
+            ops.gram(Z, zn, kid, os_, diag_add, K, n, accumulate=(g > 0))
 
     # -- factorisation with gpytorch's psd_safe_cholesky retry semantics ---------
     # The first attempt is launched WITHOUT a host synchronisation: `info` (first bad pivot per latent, like
     # cholesky_ex) and a finite-inputs flag are copied to pinned memory behind the factorisation and an event is
     # recorded.  The caller queues everything that follows (solves, inverse, sweep) and only then waits for that
     # event, so the GPU queue never drains; the jitter retry -- the rare path -- re-runs synchronously.
-    def _gram_potrf_launch(self, ws, Z, zn, kid, os_, noise, n):
-        q = Z.shape[0]
+    def _gram_potrf_launch(self, ws, comps, scaled, noise, n):
+        q = noise.shape[0]
         K, dinv, info = ws["K"], ws["dinv"], ws["info"]
         # psd_safe_cholesky refuses a matrix with NaN entries before it factors anything.  Every entry of K is a
         # function of zn, Z, the outputscale and the noise, so the O(qn) inputs are checked instead of the n^2
         # matrix (the integer tensor path would turn a NaN into an arbitrary finite number, not propagate it).
-        finite = torch.isfinite(zn).all() & torch.isfinite(noise).all()
-        if os_ is not None:
-            finite = finite & torch.isfinite(os_).all()
+        finite = torch.isfinite(noise).all()
+        for (kid, dims, ell, os_), (Z, zn, _, _) in zip(comps, scaled):
+            finite = finite & torch.isfinite(zn).all()
+            if os_ is not None:
+                finite = finite & torch.isfinite(os_).all()
         self.generation += 1
-        ops.gram(Z, zn, kid, os_, noise, K, n)
+        self._gram_all(comps, scaled, noise, K, n)
         self._mark("gram")
         ops.potrf(K, dinv, info[:q], self.cfg_main)
         info[q:] = (~finite).to(torch.int32)
@@ -191,10 +225,10 @@ class LatentEngine:
         self._mark("potrf")
         return ev
 
-    def _gram_potrf_resolve(self, ev, ws, Z, zn, kid, os_, noise, n, max_tries):
+    def _gram_potrf_resolve(self, ev, ws, comps, scaled, noise, n, max_tries):
         """Wait for the factorisation's status; returns True if a jitter retry re-factorised K (everything
         queued after the first attempt must then be redone)."""
-        q = Z.shape[0]
+        q = noise.shape[0]
         K, dinv, info = ws["K"], ws["dinv"], ws["info"]
         ev.synchronize()
         host = self._pinned.clone()
@@ -205,7 +239,7 @@ class LatentEngine:
         if not bool(bad.any()):
             self.last_jitter = None
             return False
-        jitter = torch.zeros(q, dtype=torch.float64, device=Z.device)
+        jitter = torch.zeros(q, dtype=torch.float64, device=noise.device)
         base = settings.cholesky_jitter.value()
         prev_bad = bad
         new = 0.0
@@ -223,7 +257,7 @@ class LatentEngine:
                     jitter[l] = new
                 sl = slice(l, l + 1)
                 da = (noise[sl] + jitter[sl]).contiguous()
-                ops.gram(Z[sl], zn[sl], kid, None if os_ is None else os_[sl], da, K[sl], n)
+                self._gram_all(comps, scaled, da, K[sl], n, sl)
                 ops.potrf(K[sl], dinv[sl], info[sl], self.cfg_main)
             first = False
             now = info[:q].cpu()
@@ -234,24 +268,24 @@ class LatentEngine:
                 return True
         raise NotPSDError(f"Matrix not positive definite after repeatedly adding jitter up to {new:.1e}.")
 
-    def _gram_potrf(self, ws, Z, zn, kid, os_, noise, n, max_tries):
-        ev = self._gram_potrf_launch(ws, Z, zn, kid, os_, noise, n)
-        self._gram_potrf_resolve(ev, ws, Z, zn, kid, os_, noise, n, max_tries)
+    def _gram_potrf(self, ws, comps, scaled, noise, n, max_tries):
+        ev = self._gram_potrf_launch(ws, comps, scaled, noise, n)
+        self._gram_potrf_resolve(ev, ws, comps, scaled, noise, n, max_tries)
 
     # -- training: log-probabilities and all partial gradients -------------------
-    def log_prob_and_grads(self, X, TY, ell, os_, noise, kid, need_grad, max_tries=None):
-        """lp [q] = log N(TY_l; 0, o_l k_l(X,X) + noise_l I) and, if need_grad,
-        (dlp/dTY [q,n], dlp/dell [q,d], dlp/dos [q]|None, dlp/dnoise [q])."""
+    def log_prob_and_grads(self, X, TY, comps, noise, need_grad, max_tries=None):
+        """lp [q] = log N(TY_l; 0, sum_g o_gl k_gl(X,X) + noise_l I) for comps = [(kernel id, dims, ell [q, d_g],
+        os [q] | None)] and, if need_grad, (dlp/dTY [q,n], dlp/dnoise [q], [dlp/dell_0, (dlp/dos_0), dlp/dell_1, ...])."""
         if max_tries is None:
             max_tries = settings.cholesky_max_tries.value()
         n, d = X.shape
-        q = ell.shape[0]
+        q = noise.shape[0]
         ws = self.workspace(X.device, q, n)
         np_ = ws["K"].shape[1]
         mark = self._mark
         mark("start")
-        Z, zn = ops.scale_inputs(X, self.xmean(X), ell, np_)
-        ev = self._gram_potrf_launch(ws, Z, zn, kid, os_, noise, n)
+        scaled = self._scaled(X, comps, np_)
+        ev = self._gram_potrf_launch(ws, comps, scaled, noise, n)
         K, dinv = ws["K"], ws["dinv"]
 
         def rest():
@@ -268,12 +302,18 @@ class LatentEngine:
             ops.trtri(K, dinv, self.cfg_kinv)
             ops.lauum(K, self.cfg_kinv)
             mark("potri")
-            g_ell, g_os, g_noise = ops.grad_sweep(K, alpha, Z, zn, ell, kid, os_, n)
+            g_noise, g_tensors = None, []
+            for (kid, dims, ell, os_), (Z, zn, _, _) in zip(comps, scaled):   # one sweep of K^-1 per additive component
+                g_ell, g_os, g_n = ops.grad_sweep(K, alpha, Z, zn, ell, kid, os_, n)
+                g_noise = g_n if g_noise is None else g_noise
+                g_tensors.append(g_ell)
+                if os_ is not None:
+                    g_tensors.append(g_os)
             mark("grad_sweep")
-            return lp, (-alpha, g_ell, (g_os if os_ is not None else None), g_noise)
+            return lp, (-alpha, g_noise, g_tensors)
 
         out = rest()                      # queued behind the factorisation before its status is known
-        if self._gram_potrf_resolve(ev, ws, Z, zn, kid, os_, noise, n, max_tries):
+        if self._gram_potrf_resolve(ev, ws, comps, scaled, noise, n, max_tries):
             mark("retry")
             out = rest()                  # a jitter retry re-factorised K: redo what depended on it
         return out
@@ -298,27 +338,27 @@ class LatentEngine:
         return out
 
     # -- dense noisy train covariance (kernel_cond, projected_lmc.py:367-369; small n only) --------
-    def dense_gram(self, X, ell, os_, noise, kid):
+    def dense_gram(self, X, comps, noise):
         n, d = X.shape
-        q = ell.shape[0]
+        q = noise.shape[0]
         ws = self.workspace(X.device, q, n)
         np_ = ws["K"].shape[1]
-        Z, zn = ops.scale_inputs(X, self.xmean(X), ell, np_)
+        scaled = self._scaled(X, comps, np_)
         self.generation += 1
-        ops.gram(Z, zn, kid, os_, noise, ws["K"], n)
+        self._gram_all(comps, scaled, noise, ws["K"], n)
         K = ws["K"][:, :n, :n]
         return torch.tril(K) + torch.tril(K, -1).transpose(1, 2)
 
     # -- leave-one-out by-product (projected_lmc.py:1108-1119) ----------------------
-    def loo(self, X, TY, ell, os_, noise, kid, max_tries=None):
+    def loo(self, X, TY, comps, noise, max_tries=None):
         if max_tries is None:
             max_tries = settings.cholesky_max_tries.value()
         n, d = X.shape
-        q = ell.shape[0]
+        q = noise.shape[0]
         ws = self.workspace(X.device, q, n)
         np_ = ws["K"].shape[1]
-        Z, zn = ops.scale_inputs(X, self.xmean(X), ell, np_)
-        self._gram_potrf(ws, Z, zn, kid, os_, noise, n, max_tries)
+        scaled = self._scaled(X, comps, np_)
+        self._gram_potrf(ws, comps, scaled, noise, n, max_tries)
         K, dinv = ws["K"], ws["dinv"]
         _, alpha, _, _ = ops.solve_logdet(K, dinv, TY, n, ws["rhs"])
         self.generation += 1
@@ -327,20 +367,23 @@ class LatentEngine:
         return sigma2, alpha * sigma2
 
     # -- prediction -----------------------------------------------------------------
-    def factorize(self, X, TY, ell, os_, noise, kid, max_tries=None):
-        """Prediction cache: L (in ws['K']), dinv, alpha, scaled inputs."""
+    def factorize(self, X, TY, comps, noise, max_tries=None):
+        """Prediction cache: L (in ws['K']), dinv, alpha, scaled inputs of every kernel component."""
         if max_tries is None:
             max_tries = settings.cholesky_max_tries.value()
         n, d = X.shape
-        q = ell.shape[0]
+        q = noise.shape[0]
         ws = self.workspace(X.device, q, n)
         np_ = ws["K"].shape[1]
-        xmean = self.xmean(X)
-        Z, zn = ops.scale_inputs(X, xmean, ell, np_)
-        self._gram_potrf(ws, Z, zn, kid, os_, noise, n, max_tries)
+        scaled = self._scaled(X, comps, np_)
+        self._gram_potrf(ws, comps, scaled, noise, n, max_tries)
         _, alpha, _, _ = ops.solve_logdet(ws["K"], ws["dinv"], TY, n, ws["rhs"])
-        return dict(L=ws["K"], dinv=ws["dinv"], alpha=alpha, Z=Z, zn=zn, xmean=xmean, ell=ell, os=os_, kid=kid, n=n,
-                    d=d, q=q, generation=self.generation)
+        prior_var = None                      # k(x*, x*) = sum_g os_g k_g(0) = sum_g os_g (1 without a ScaleKernel)
+        for kid, dims, ell, os_ in comps:
+            v = torch.ones(q, dtype=torch.float64, device=X.device) if os_ is None else os_
+            prior_var = v if prior_var is None else prior_var + v
+        return dict(L=ws["K"], dinv=ws["dinv"], alpha=alpha, comps=comps, scaled=scaled, prior_var=prior_var.contiguous(),
+                    n=n, d=d, q=q, generation=self.generation)
 
     def state_is_current(self, st) -> bool:
         """False once anything (training step, compute_loo, kernel_cond, another factorize) has rewritten the
@@ -372,10 +415,14 @@ class LatentEngine:
             if Kx is None or Kx.shape[2] != mt:
                 Kx = None
                 Kx = torch.empty((q, np_, mt), dtype=torch.float64, device=dev)
-            Zt, znt = ops.scale_inputs(Xs[s0:s0 + cnt].contiguous(), st["xmean"], st["ell"], mt)
-            ops.cross_gram(st["Z"], st["zn"], Zt, znt, st["kid"], st["os"], Kx, n, mt)
+            xs = Xs[s0:s0 + cnt]
+            for g, ((kid, dims, ell, os_), (Z, zn, _, xm)) in enumerate(zip(st["comps"], st["scaled"])):
+                xg = xs if len(dims) == xs.shape[1] and tuple(dims) == tuple(range(xs.shape[1])) else \
+                    xs.index_select(1, torch.as_tensor(list(dims), device=dev))
+                Zt, znt = ops.scale_inputs(xg.contiguous(), xm, ell, mt)
+                ops.cross_gram(Z, zn, Zt, znt, kid, os_, Kx, n, mt, accumulate=(g > 0))
             lat_mean[:, s0:s0 + cnt] = ops.latent_mean(Kx, st["alpha"], n, mt)[:, :cnt]
             if need_var:
                 ops.trsm(2, st["L"], st["dinv"], Kx, 1.0, self.cfg_main)
-                lat_var[:, s0:s0 + cnt] = ops.latent_var(Kx, st["os"], mt)[:, :cnt]
+                lat_var[:, s0:s0 + cnt] = ops.latent_var(Kx, st["prior_var"], mt)[:, :cnt]
         return lat_mean, lat_var

@@ -23,26 +23,34 @@ class ProjectData(torch.autograd.Function):
 
 
 class LatentLogProb(torch.autograd.Function):
-    """lp_l = log N(TY_l; 0, o_l k_l(X,X) + noise_l I), batched over latents (kernels 2-4).
+    """lp_l = log N(TY_l; 0, sum_g o_gl k_gl(X,X) + noise_l I), batched over latents (kernels 2-4).
 
-    The backward quantities are produced eagerly in forward (K -> L -> K^-1 is done in
-    place in one cached workspace, so nothing of size n^2 is saved for backward)."""
+    ``spec`` = ((kernel id, active dims, has outputscale), ...) describes the additive kernel; ``tensors`` are its
+    parameters in order (ell_0 [q, d_0], os_0 [q] if any, ell_1, ...).  The backward quantities are produced
+    eagerly in forward (K -> L -> K^-1 is done in place in one cached workspace, so nothing of size n^2 is saved
+    for backward)."""
 
     @staticmethod
-    def forward(ctx, engine, X, kid, TY, ell, os_, noise):
-        need = any(t is not None and t.requires_grad for t in (TY, ell, os_, noise))
-        lp, grads = engine.log_prob_and_grads(
-            X, TY.detach().contiguous(), ell.detach().contiguous(),
-            None if os_ is None else os_.detach().contiguous(), noise.detach().contiguous(), kid, need)
+    def forward(ctx, engine, X, spec, TY, noise, *tensors):
+        need = any(t is not None and t.requires_grad for t in (TY, noise, *tensors))
+        comps, i = [], 0
+        for kid, dims, has_os in spec:
+            ell = tensors[i].detach().contiguous()
+            i += 1
+            os_ = None
+            if has_os:
+                os_ = tensors[i].detach().contiguous()
+                i += 1
+            comps.append((kid, dims, ell, os_))
+        lp, grads = engine.log_prob_and_grads(X, TY.detach().contiguous(), comps, noise.detach().contiguous(), need)
         ctx.grads = grads
-        ctx.has_os = os_ is not None
         return lp
 
     @staticmethod
     def backward(ctx, go):
         if ctx.grads is None:
             raise RuntimeError("LatentLogProb.backward called but no input required grad in forward")
-        g_ty, g_ell, g_os, g_noise = ctx.grads
+        g_ty, g_noise, g_tensors = ctx.grads
         ctx.grads = None
-        return (None, None, None, g_ty * go[:, None], g_ell * go[:, None],
-                (g_os * go) if ctx.has_os else None, g_noise * go)
+        out = [(g * go[:, None]) if g.dim() == 2 else (g * go) for g in g_tensors]
+        return (None, None, None, g_ty * go[:, None], g_noise * go, *out)

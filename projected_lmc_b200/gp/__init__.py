@@ -2,4 +2,4 @@
 
 Usage mirrors the reference (``import gpytorch as gp``):
 ``from projected_lmc_b200 import gp; gp.kernels.MaternKernel``."""
-from . import constraints, distributions, kernels, likelihoods, means, mlls, settings  # noqa: F401
+from . import constraints, distributions, kernels, likelihoods, means, mlls, priors, settings  # noqa: F401

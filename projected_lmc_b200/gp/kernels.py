@@ -21,11 +21,19 @@ class Kernel(torch.nn.Module):
         self.ard_num_dims = ard_num_dims
         self.batch_shape = torch.Size(batch_shape)
         self.active_dims = None if active_dims is None else tuple(active_dims)
-        if lengthscale_prior is not None:
-            raise NotImplementedError("lengthscale priors are outside the B200 hot-path scope (SURVEY.md 8a row a3)")
         d = 1 if ard_num_dims is None else ard_num_dims
         self.register_parameter("raw_lengthscale", torch.nn.Parameter(torch.zeros(*self.batch_shape, 1, d)))
         self.raw_lengthscale_constraint = lengthscale_constraint if lengthscale_constraint is not None else Positive()
+        # gpytorch: register_prior("lengthscale_prior", prior, lambda m: m.lengthscale, ...): the log-density of the
+        # constrained lengthscale is added to the MLL by ExactMarginalLogLikelihood._add_other_terms
+        self.lengthscale_prior = lengthscale_prior
+
+    def named_priors(self, prefix=""):
+        if self.lengthscale_prior is not None:
+            yield prefix + "lengthscale_prior", self, self.lengthscale_prior, (lambda m: m.lengthscale)
+
+    def __add__(self, other):
+        return AdditiveKernel(*_flatten(self), *_flatten(other))
 
     @property
     def lengthscale(self) -> torch.Tensor:
@@ -76,3 +84,50 @@ class ScaleKernel(torch.nn.Module):
     @property
     def kernel_id(self):
         return self.base_kernel.kernel_id
+
+    @property
+    def active_dims(self):
+        return self.base_kernel.active_dims
+
+    def named_priors(self, prefix=""):
+        yield from self.base_kernel.named_priors(prefix + "base_kernel.")
+
+    def __add__(self, other):
+        return AdditiveKernel(*_flatten(self), *_flatten(other))
+
+
+class InducingPointKernel(torch.nn.Module):
+    """gpytorch.kernels.InducingPointKernel(base_kernel, inducing_points, likelihood): parameter holder
+    (``inducing_points`` [m, d], shared by the latents); the SGPR arithmetic lives in projected_lmc_b200/sgpr.py."""
+
+    def __init__(self, base_kernel, inducing_points, likelihood, **kwargs):
+        super().__init__()
+        self.base_kernel = base_kernel
+        self.likelihood = likelihood
+        if inducing_points.dim() == 1:
+            inducing_points = inducing_points.unsqueeze(-1)
+        self.register_parameter("inducing_points", torch.nn.Parameter(inducing_points))
+
+    def named_priors(self, prefix=""):
+        yield from self.base_kernel.named_priors(prefix + "base_kernel.")
+
+
+def _flatten(k):
+    return list(k.kernels) if isinstance(k, AdditiveKernel) else [k]
+
+
+class AdditiveKernel(torch.nn.Module):
+    """k(x, x') = sum_g k_g(x, x'): what ``covar_module += ScaleKernel(...)`` builds in handle_covar_
+    (projected_lmc.py:159-162).  ``kernels`` is a ModuleList like gpytorch's, so parameter names match
+    (``covar_module.kernels.<g>.base_kernel.raw_lengthscale`` ...)."""
+
+    def __init__(self, *kernels):
+        super().__init__()
+        self.kernels = torch.nn.ModuleList(kernels)
+
+    def named_priors(self, prefix=""):
+        for i, k in enumerate(self.kernels):
+            yield from k.named_priors(f"{prefix}kernels.{i}.")
+
+    def __add__(self, other):
+        return AdditiveKernel(*_flatten(self), *_flatten(other))

@@ -18,6 +18,16 @@ class ExactMarginalLogLikelihood(MarginalLogLikelihood):
         super().__init__(likelihood, model)
 
     def _add_other_terms(self, res, params):
-        # added-loss terms exist only for inducing-point kernels and log-priors only
-        # with prior_scales (projected_lmc.py:135-149); both are out of scope here.
+        """gpytorch 1.11 ExactMarginalLogLikelihood._add_other_terms: added-loss terms of the model (only the
+        inducing-point kernel has one) and the log-density of every registered prior (only the lengthscale priors of
+        handle_covar_, projected_lmc.py:135-149).  As in gpytorch, each SUMMED prior term is added to the whole
+        [q]-shaped result -- every latent's entry receives it -- so after the caller's ``.sum()`` it counts q times;
+        the reference inherits that, and so does this."""
+        model = self.model
+        if hasattr(model, "added_loss_terms"):
+            for term in model.added_loss_terms():
+                res = res + term.loss(*params)
+        if hasattr(model, "named_priors"):
+            for _, module, prior, closure in model.named_priors():
+                res = res + prior.log_prob(closure(module)).sum()
         return res

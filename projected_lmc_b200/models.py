@@ -28,22 +28,46 @@ from .mixing import (LMCMixingMatrix, LowerTriangularParam, PositiveDiagonalPara
 def handle_covar_(kernel, dim: int, decomp: Optional[List[List[int]]] = None, n_funcs: int = 1,
                   prior_scales: Optional[Tensor] = None, prior_width: Optional[Tensor] = None,
                   outputscales: bool = True, ker_kwargs: Optional[dict] = None):
-    """Kernel factory: one ARD kernel over all ``dim`` inputs with batch shape [n_funcs],
-    wrapped in a ScaleKernel when ``outputscales``.  Additive ``decomp`` kernels and
-    lengthscale priors are outside the accelerated path."""
+    """Kernel factory (drop-in for handle_covar_, projected_lmc.py:107-181): ARD kernels with batch shape
+    [n_funcs].  ``decomp`` = groups of input dimensions, one sub-kernel per group, each wrapped in a ScaleKernel and
+    summed (``decomp = [[0,1],[1,2]]`` -> k1(x0,x1) + k2(x1,x2)); ``prior_scales`` / ``prior_width`` put a Normal
+    (one dimension) or MultivariateNormal (several; covariance diag(scale*width) exactly as the reference writes it)
+    prior on each group's lengthscales and initialise them at the prior mean."""
     ker_kwargs = {} if ker_kwargs is None else ker_kwargs
-    full = list(range(dim))
-    if decomp is not None and [list(g) for g in decomp] != [full]:
-        raise NotImplementedError("additive `decomp` kernels are not part of the B200 hot path")
+    if decomp is None:
+        decomp = [list(range(dim))]
+    l_priors = [None] * len(decomp)
     if prior_scales is not None:
         if prior_width is None:
             raise ValueError('A prior width should be provided if a prior mean is')
-        raise NotImplementedError("lengthscale priors are not part of the B200 hot path")
-    base = kernel(ard_num_dims=dim, active_dims=full, lengthscale_prior=None, batch_shape=torch.Size([n_funcs]),
-                  **ker_kwargs)
-    if outputscales:
-        return gp.kernels.ScaleKernel(base, batch_shape=torch.Size([n_funcs]))
-    return base
+        if type(prior_scales) is not list:   # an array with one length per variable, or a list with one array per kernel
+            prior_scales = [prior_scales[idx_list] for idx_list in decomp]
+        if type(prior_width) is not list:
+            prior_width = [prior_width[idx_list] for idx_list in decomp]
+        for i_ker, idx_list in enumerate(decomp):
+            if len(idx_list) > 1:
+                l_priors[i_ker] = gp.priors.MultivariateNormalPrior(
+                    loc=prior_scales[i_ker], covariance_matrix=torch.diag_embed(prior_scales[i_ker] * prior_width[i_ker]))
+            else:
+                l_priors[i_ker] = gp.priors.NormalPrior(loc=prior_scales[i_ker],
+                                                        scale=prior_scales[i_ker] * prior_width[i_ker])
+    kernels = [kernel(ard_num_dims=len(idx_list), active_dims=idx_list, lengthscale_prior=l_priors[i_ker],
+                      batch_shape=torch.Size([n_funcs]), **ker_kwargs) for i_ker, idx_list in enumerate(decomp)]
+    if len(decomp) > 1:
+        covar_module = gp.kernels.ScaleKernel(kernels[0], batch_shape=torch.Size([n_funcs]))
+        for ker in kernels[1:]:
+            covar_module += gp.kernels.ScaleKernel(ker, batch_shape=torch.Size([n_funcs]))
+    elif outputscales:
+        covar_module = gp.kernels.ScaleKernel(kernels[0], batch_shape=torch.Size([n_funcs]))
+    else:
+        covar_module = kernels[0]
+    if prior_scales is not None and kernels[0].has_lengthscale:
+        try:
+            for i_ker in range(len(kernels)):
+                kernels[i_ker].lengthscale = l_priors[i_ker].mean
+        except Exception:
+            raise ValueError('Provided prior scales were of the wrong shape')
+    return covar_module
 
 
 def init_lmc_coefficients(train_y: Tensor, n_latents: int, QR_form: bool = False):
@@ -93,7 +117,8 @@ class ExactGPModel(torch.nn.Module):
                                           prior_scales=prior_scales, prior_width=prior_width,
                                           outputscales=outputscales, n_funcs=n_tasks, ker_kwargs=ker_kwargs)
         if n_inducing_points is not None:
-            raise NotImplementedError("inducing-point (SGPR) kernels are not part of the B200 hot path (SURVEY 8f)")
+            self.covar_module = gp.kernels.InducingPointKernel(self.covar_module,
+                                                              torch.randn(n_inducing_points, self.dim), likelihood)
 
     # gpytorch.models.ExactGP moves its training data together with the module
     def _apply(self, fn, *args, **kwargs):
@@ -101,20 +126,65 @@ class ExactGPModel(torch.nn.Module):
         self.train_targets = fn(self.train_targets)
         return super()._apply(fn, *args, **kwargs)
 
+    def named_priors(self):
+        """(name, module, prior, closure) of every registered prior (gpytorch Module.named_priors)."""
+        yield from self.covar_module.named_priors("covar_module.")
+
+    def _inducing(self):
+        """The inducing-point kernel wrapper, or None for the exact model."""
+        cm = self.covar_module
+        return cm if isinstance(cm, gp.kernels.InducingPointKernel) else None
+
+    def _covar(self):
+        """The kernel proper (under the inducing-point wrapper, if any)."""
+        cm = self.covar_module
+        return cm.base_kernel if isinstance(cm, gp.kernels.InducingPointKernel) else cm
+
+    def added_loss_terms(self):
+        """gpytorch Module.added_loss_terms: the inducing-point kernel registers one during the training-mode
+        forward; it is evaluated together with the latent log-probabilities and handed out here."""
+        if self._inducing() is not None and getattr(self, "_sgpr_added", None) is not None:
+            yield _StoredLoss(self._sgpr_added)
+
     def _base_kernel(self):
-        return self.covar_module.base_kernel if hasattr(self.covar_module, 'base_kernel') else self.covar_module
+        """The (first) ARD kernel under the optional ScaleKernel / sum."""
+        cm = self._covar()
+        if hasattr(cm, 'kernels'):
+            cm = cm.kernels[0]
+        return cm.base_kernel if hasattr(cm, 'base_kernel') else cm
+
+    def _kernel_components(self):
+        """[(kernel_id, active dims, lengthscale [q, d_g], outputscale [q] | None)] of the additive kernel."""
+        cm = self._covar()
+        out = []
+        for ker in (cm.kernels if hasattr(cm, 'kernels') else [cm]):
+            base = ker.base_kernel if hasattr(ker, 'base_kernel') else ker
+            dims = tuple(range(self.dim)) if base.active_dims is None else tuple(base.active_dims)
+            out.append((base.kernel_id, dims, base.lengthscale.squeeze(-2),
+                        ker.outputscale if hasattr(ker, 'base_kernel') else None))
+        return out
 
     def lscales(self, unpacked: bool = True) -> Union[List[Tensor], Tensor]:
-        """Learned lengthscales, n_tasks x n_dims (list-wrapped when ``unpacked=False``)."""
+        """Learned lengthscales: one n_funcs x n_dims tensor per sub-kernel (a single tensor for a non-composite
+        kernel when ``unpacked``), as projected_lmc.py:324-346."""
+        if hasattr(self._covar(), 'kernels'):
+            return [(k.base_kernel if hasattr(k, 'base_kernel') else k).lengthscale.data.squeeze()
+                    for k in self._covar().kernels]
         scales = self._base_kernel().lengthscale.data.squeeze()
         return scales if unpacked else [scales]
 
     def outputscale(self, unpacked: bool = False) -> Tensor:
-        """Learned outputscales, n_funcs x n_kernels; raises when the model has none."""
+        """Learned outputscales, n_funcs x n_kernels; raises when the model has none (projected_lmc.py:348-365)."""
+        cm = self._covar()
+        n_kernels = len(cm.kernels) if hasattr(cm, 'kernels') else 1
         n_funcs = self.n_latents if hasattr(self, 'n_latents') else self.n_tasks
-        res = torch.zeros((n_funcs, 1))
-        res[:, 0] = self.covar_module.outputscale.data.squeeze()
-        return res.squeeze() if unpacked else res
+        res = torch.zeros((n_funcs, n_kernels))
+        if n_kernels > 1:
+            for i_ker in range(n_kernels):
+                res[:, i_ker] = cm.kernels[i_ker].outputscale.data.squeeze()
+        else:
+            res[:, 0] = cm.outputscale.data.squeeze()
+        return res.squeeze() if (n_kernels == 1 and unpacked) else res
 
 
 def _resolve_kernel(kernel_type):
@@ -285,19 +355,36 @@ class ProjectedGPModel(ExactGPModel):
         return res
 
     # ---- CUDA path -----------------------------------------------------------------
-    def _kernel_params(self):
-        base = self._base_kernel()
-        ell = base.lengthscale.squeeze(-2)                      # [q, d]
-        os_ = self.covar_module.outputscale if hasattr(self.covar_module, 'base_kernel') else None
-        return base.kernel_id, ell, os_, self.projected_noise()
+    def _local_components(self, detach=False):
+        """(spec, tensors) of the kernel for the latents owned by this process: spec = ((kernel id, dims, has
+        outputscale), ...), tensors = [ell_0, (os_0), ell_1, ...] as contiguous float64."""
+        lo, hi = self._latent_range
+        spec, tensors = [], []
+        for kid, dims, ell, os_ in self._kernel_components():
+            spec.append((kid, dims, os_ is not None))
+            tensors.append(_as_f64(ell)[lo:hi])
+            if os_ is not None:
+                tensors.append(_as_f64(os_)[lo:hi])
+        if detach:
+            tensors = [t.detach().contiguous() for t in tensors]
+        return tuple(spec), tensors
 
     def _latent_log_prob(self, proj_target: Tensor) -> Tensor:
         """log N(TY_l; 0, K_l + noise_l I) for the latents owned by this process."""
         X = _as_f64(self.train_inputs[0])
-        kid, ell, os_, noise = self._kernel_params()
         lo, hi = self._latent_range
-        lp = LatentLogProb.apply(self._engine, X, kid, _as_f64(proj_target)[lo:hi], _as_f64(ell)[lo:hi],
-                                 None if os_ is None else _as_f64(os_)[lo:hi], _as_f64(noise)[lo:hi])
+        spec, tensors = self._local_components()
+        ind = self._inducing()
+        if ind is not None:     # SGPR: low-rank covariance K_fu K_uu^-1 K_uf + noise, plus the added loss term
+            from . import sgpr
+            self._engine.xmean(X)
+            lp, added = sgpr.latent_log_prob(self._engine, X, _as_f64(proj_target)[lo:hi].contiguous(),
+                                             _as_f64(ind.inducing_points), ops_components(spec, tensors),
+                                             _as_f64(self.projected_noise())[lo:hi])
+            self._sgpr_added = added
+            return lp.to(proj_target.dtype)
+        lp = LatentLogProb.apply(self._engine, X, spec, _as_f64(proj_target)[lo:hi],
+                                 _as_f64(self.projected_noise())[lo:hi], *tensors)
         return lp.to(proj_target.dtype)
 
     def forward(self, x: Tensor):
@@ -317,17 +404,30 @@ class ProjectedGPModel(ExactGPModel):
         key = tuple((id(p), p._version) for p in self.parameters()) + (self.train_y._version, self._latent_range)
         # the factor lives in the engine's shared workspace: compute_loo / kernel_cond / a training-mode handle
         # rewrite it, so the cache is also checked against the engine's workspace generation
-        if self._pred_cache is None or self._pred_key != key or not self._engine.state_is_current(self._pred_cache):
+        stale = self._inducing() is None and not self._engine.state_is_current(self._pred_cache)
+        if self._pred_cache is None or self._pred_key != key or stale:
             with torch.no_grad():
                 X = _as_f64(self.train_inputs[0])
-                kid, ell, os_, noise = self._kernel_params()
                 lo, hi = self._latent_range
+                spec, tensors = self._local_components(detach=True)
                 TY = _as_f64(self.project_data(self.train_y))[lo:hi].contiguous()
-                self._pred_cache = self._engine.factorize(
-                    X, TY, _as_f64(ell)[lo:hi].contiguous(), None if os_ is None else _as_f64(os_)[lo:hi].contiguous(),
-                    _as_f64(noise)[lo:hi].contiguous(), kid)
+                noise = _as_f64(self.projected_noise())[lo:hi].contiguous()
+                if self._inducing() is not None:
+                    from . import sgpr
+                    self._engine.xmean(X)
+                    self._pred_cache = sgpr.prediction_state(
+                        self._engine, X, TY, _as_f64(self._inducing().inducing_points).detach().contiguous(),
+                        ops_components(spec, tensors), noise)
+                else:
+                    self._pred_cache = self._engine.factorize(X, TY, ops_components(spec, tensors), noise)
                 self._pred_key = key
         return self._pred_cache
+
+    def _predict_latents(self, st, xs):
+        if self._inducing() is not None:
+            from . import sgpr
+            return sgpr.predict_latents(self._engine, st, _as_f64(self.train_inputs[0]), xs)
+        return self._engine.predict_latents(st, xs)
 
     def train(self, mode: bool = True):
         if mode:
@@ -343,17 +443,16 @@ class ProjectedGPModel(ExactGPModel):
         with torch.no_grad():
             st = self._prediction_state()
             xs = _as_f64(x if x.dim() > 1 else x.unsqueeze(-1)).contiguous()
-            m, v = self._engine.predict_latents(st, xs)
+            m, v = self._predict_latents(st, xs)
         return LatentPosterior(m.to(x.dtype), v.to(x.dtype))
 
     def kernel_cond(self):
         """Condition numbers of the noisy latent train covariances K_l + s_l I (dense SVD: small n)."""
         with torch.no_grad():
             X = _as_f64(self.train_inputs[0])
-            kid, ell, os_, noise = self._kernel_params()
-            K = self._engine.dense_gram(X, _as_f64(ell).contiguous(),
-                                        None if os_ is None else _as_f64(os_).contiguous(),
-                                        _as_f64(noise).contiguous(), kid)
+            comps = [(kid, dims, _as_f64(ell).contiguous(), None if os_ is None else _as_f64(os_).contiguous())
+                     for kid, dims, ell, os_ in self._kernel_components()]
+            K = self._engine.dense_gram(X, comps, _as_f64(self.projected_noise()).contiguous())
             return torch.linalg.cond(K)
 
     def compute_loo(self, output=None):
@@ -361,11 +460,10 @@ class ProjectedGPModel(ExactGPModel):
         both n_points x n_latents (by-product of K^-1 and alpha)."""
         with torch.no_grad():
             X = _as_f64(self.train_inputs[0])
-            kid, ell, os_, noise = self._kernel_params()
+            comps = [(kid, dims, _as_f64(ell).contiguous(), None if os_ is None else _as_f64(os_).contiguous())
+                     for kid, dims, ell, os_ in self._kernel_components()]
             TY = _as_f64(self.project_data(self.train_y)).contiguous()
-            s2, r = self._engine.loo(X, TY, _as_f64(ell).contiguous(),
-                                     None if os_ is None else _as_f64(os_).contiguous(),
-                                     _as_f64(noise).contiguous(), kid)
+            s2, r = self._engine.loo(X, TY, comps, _as_f64(self.projected_noise()).contiguous())
         dt = self.train_y.dtype
         return s2.T.to(dt), r.T.to(dt)
 
@@ -385,7 +483,7 @@ class ProjectedGPModel(ExactGPModel):
             if has_bad:
                 xs = xs.clone()
                 xs[bad_rows] = 0.0
-            lat_mean, lat_var = self._engine.predict_latents(st, xs)
+            lat_mean, lat_var = self._predict_latents(st, xs)
             lo, hi = self._latent_range
             Ht = _as_f64(self.lmc_coefficients())[lo:hi].contiguous()
             ns = xs.shape[0]
@@ -405,6 +503,14 @@ class ProjectedGPModel(ExactGPModel):
         return gp.distributions.MultitaskMultivariateNormal(mean.to(x.dtype), var.to(x.dtype))
 
 
+class _StoredLoss:
+    def __init__(self, value):
+        self.value = value
+
+    def loss(self, *params):
+        return self.value
+
+
 class LatentPosterior:
     def __init__(self, mean, variance):
         self.mean, self.variance = mean, variance
@@ -412,6 +518,20 @@ class LatentPosterior:
     @property
     def stddev(self):
         return self.variance.clamp_min(0).sqrt()
+
+
+def ops_components(spec, tensors):
+    """[(kernel id, dims, ell, os | None)] from the flat (spec, tensors) form used across the autograd boundary."""
+    out, i = [], 0
+    for kid, dims, has_os in spec:
+        ell = tensors[i]
+        i += 1
+        os_ = None
+        if has_os:
+            os_ = tensors[i]
+            i += 1
+        out.append((kid, dims, ell, os_))
+    return out
 
 
 def _as_f64(t: Tensor) -> Tensor:

@@ -186,23 +186,43 @@ def scale_inputs(X, xmean, ell, rows_pad):
 
 
 @_on_device
-def gram(Z, zn, kernel_id, os_, diag_add, K, n):
+def gram(Z, zn, kernel_id, os_, diag_add, K, n, accumulate=False):
     q, np_, dp = Z.shape
     check(
         lib().plmc_gram(ptr(Z), ptr(zn), kernel_id, ptr(os_), ptr(diag_add), ptr(K), K.stride(1), K.stride(0), n, np_,
-                        dp, q, stream()),
+                        dp, q, int(accumulate), stream()),
         "gram",
     )
 
 
 @_on_device
-def cross_gram(Ztr, zntr, Zte, znte, kernel_id, os_, Kx, n, mt):
+def cross_gram(Ztr, zntr, Zte, znte, kernel_id, os_, Kx, n, mt, accumulate=False):
     q, np_, dp = Ztr.shape
     check(
         lib().plmc_cross_gram(ptr(Ztr), ptr(zntr), ptr(Zte), ptr(znte), kernel_id, ptr(os_), ptr(Kx), Kx.stride(1),
-                              Kx.stride(0), n, np_, Zte.shape[1], mt, dp, q, stream()),
+                              Kx.stride(0), n, np_, Zte.shape[1], mt, dp, q, int(accumulate), stream()),
         "cross_gram",
     )
+
+
+@_on_device
+def cross_gram_bwd(Zr, Zc, G, kernel_id, os_, ell, nr, nc):
+    """Adjoint of K[l,i,j] = os[l] k(|zr_i - zc_j|^2) for the cotangent G [q, nr, >=nc]:
+    (g_ell [q, d], g_os [q], g_rows [nr, d] summed over latents, w.r.t. the unscaled row points)."""
+    q, rpr, dp = Zr.shape
+    rpc = Zc.shape[1]
+    d = ell.shape[1]
+    dev = G.device
+    ws = torch.empty((lib().plmc_cross_gram_bwd_ws(nr, nc, d, q) // 8,), dtype=torch.float64, device=dev)
+    g_ell = torch.empty((q, d), dtype=torch.float64, device=dev)
+    g_os = torch.empty((q,), dtype=torch.float64, device=dev)
+    g_rows = torch.empty((nr, d), dtype=torch.float64, device=dev)
+    check(
+        lib().plmc_cross_gram_bwd(ptr(Zr), rpr, ptr(Zc), rpc, ptr(G), G.stride(1), G.stride(0), kernel_id, ptr(os_),
+                                  ptr(ell), ptr(g_ell), ptr(g_os), ptr(g_rows), ptr(ws), nr, nc, d, dp, q, stream()),
+        "cross_gram_bwd",
+    )
+    return g_ell, g_os, g_rows
 
 
 @_on_device

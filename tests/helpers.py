@@ -59,13 +59,33 @@ def oracle_params(m_cpu) -> O.OracleParams:
     """Effective tensors of a CPU copy of the model, still attached to its raw leaf parameters."""
     base = m_cpu._base_kernel()
     lmc = m_cpu.lmc_coefficients
+    comps = None
+    cov = m_cpu._covar()
+    if hasattr(cov, "kernels") or base.lengthscale_prior is not None or base.active_dims not in (
+            None, tuple(range(m_cpu.dim))):
+        comps = []
+        cm = cov
+        for ker in (cm.kernels if hasattr(cm, "kernels") else [cm]):
+            b = ker.base_kernel if hasattr(ker, "base_kernel") else ker
+            pr = b.lengthscale_prior
+            loc = width = None
+            if pr is not None:
+                loc = pr.loc
+                # NormalPrior keeps the standard deviation loc*width, the multivariate one the covariance diag(loc*width)
+                width = (pr.scale / pr.loc) if hasattr(pr, "scale") else torch.diagonal(pr.covariance_matrix) / pr.loc
+            comps.append(O.OracleComponent(
+                dims=list(range(m_cpu.dim)) if b.active_dims is None else list(b.active_dims),
+                raw_lengthscale=b.raw_lengthscale,
+                raw_outputscale=ker.raw_outputscale if hasattr(ker, "base_kernel") else None,
+                prior_loc=loc, prior_width=width))
     p = O.OracleParams(
         raw_lengthscale=base.raw_lengthscale,
         raw_noise=m_cpu.likelihood.noise_covar.raw_noise,
         noise_lower=float(m_cpu.likelihood.noise_covar.raw_noise_constraint.lower_bound),
         kernel=KNAMES[base.kernel_id],
-        raw_outputscale=m_cpu.covar_module.raw_outputscale if hasattr(m_cpu.covar_module, "base_kernel") else None,
-        scalar_B=m_cpu.scalar_B, diagonal_B=m_cpu.diagonal_B, eps=m_cpu.eps,
+        raw_outputscale=cov.raw_outputscale if (hasattr(cov, "base_kernel") and not hasattr(cov, "kernels")) else None,
+        scalar_B=m_cpu.scalar_B, diagonal_B=m_cpu.diagonal_B, eps=m_cpu.eps, components=comps,
+        inducing_points=m_cpu._inducing().inducing_points if m_cpu._inducing() is not None else None,
     )
     if lmc.bulk:
         p.H = lmc.H

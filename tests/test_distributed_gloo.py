@@ -21,19 +21,24 @@ from .helpers import KNAMES, cpu_copy, make_model, oracle_params, rel_err, synth
 class OracleEngine:
     """Stand-in for LatentEngine with the same contract, backed by the CPU oracle."""
 
-    def log_prob_and_grads(self, X, TY, ell, os_, noise, kid, need_grad, max_tries=None):
+    def log_prob_and_grads(self, X, TY, comps, noise, need_grad, max_tries=None):
         with torch.enable_grad():  # autograd.Function.forward runs with grad mode off
-            leaves = [TY.clone().requires_grad_(), ell.clone().requires_grad_(), noise.clone().requires_grad_()]
-            if os_ is not None:
-                leaves.append(os_.clone().requires_grad_())
-            n = X.shape[0]
-            K = O.base_kernel(KNAMES[kid], X, X, leaves[1][:, None, :], zero_diag=False)
-            if os_ is not None:
-                K = K * leaves[3][:, None, None]
-            K = K + torch.diag_embed(leaves[2][:, None].expand(-1, n))
-            lp = O.mvn_log_prob(K, leaves[0])
-            g = torch.autograd.grad(lp.sum(), leaves)
-        return lp.detach(), (g[0], g[1], (g[3] if os_ is not None else None), g[2])
+            ty, nz = TY.clone().requires_grad_(), noise.clone().requires_grad_()
+            leaves, n, K = [], X.shape[0], 0.0
+            for kid, dims, ell, os_ in comps:
+                e = ell.clone().requires_grad_()
+                leaves.append(e)
+                Xg = X[:, list(dims)]
+                Kg = O.base_kernel(KNAMES[kid], Xg, Xg, e[:, None, :], zero_diag=False)
+                if os_ is not None:
+                    o = os_.clone().requires_grad_()
+                    leaves.append(o)
+                    Kg = Kg * o[:, None, None]
+                K = K + Kg
+            K = K + torch.diag_embed(nz[:, None].expand(-1, n))
+            lp = O.mvn_log_prob(K, ty)
+            g = torch.autograd.grad(lp.sum(), [ty, nz] + leaves)
+        return lp.detach(), (g[0], g[1], list(g[2:]))
 
 
 def _patch_kernels():

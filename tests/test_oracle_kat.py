@@ -1,5 +1,7 @@
 """Known-answer tests of the oracle (CPU): dependency-free identities, see oracle/kat.py."""
 import math
+
+import numpy as np
 import warnings
 
 import pytest
@@ -145,3 +147,91 @@ def test_psd_safe_cholesky_jitter_schedule_matches_the_published_one():
     assert torch.allclose(jit, jit[0].expand_as(jit), rtol=1e-6, atol=1e-16)
     ratio = math.log10(jit[0].item() / 1e-8)
     assert abs(ratio - round(ratio)) < 1e-3 and 0 <= round(ratio) <= 5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# handle_covar_ extras (projected_lmc.py:131-181): additive `decomp` kernels and lengthscale priors
+# ---------------------------------------------------------------------------------------------------------------
+def test_additive_kernel_matches_scikit_learn_sum_kernel():
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern
+
+    g = torch.Generator().manual_seed(11)
+    X = torch.rand(31, 4, generator=g) * 2 - 1
+    Y = torch.randn(31, 5, generator=g)
+    m = make_model(X, Y, 2, variant="PLMC", kernel="matern52", decomp=[[0, 1], [1, 2, 3]])
+    p = oracle_params(m)
+    assert p.components is not None and len(p.components) == 2
+    with torch.no_grad():
+        K = O.gram(p, X, training=False)
+    for l in range(2):
+        ref = 0.0
+        for c in p.components:
+            ell = O.softplus(c.raw_lengthscale)[l, 0].detach().numpy()
+            os_ = float(O.softplus(c.raw_outputscale)[l])
+            ref = ref + (ConstantKernel(os_) * Matern(length_scale=ell, nu=2.5))(X[:, c.dims].numpy())
+        assert abs(K[l].numpy() - ref).max() < 1e-12
+
+
+def test_lengthscale_prior_densities_match_scipy_and_count_q_times():
+    from scipy.stats import multivariate_normal, norm
+
+    g = torch.Generator().manual_seed(12)
+    X = torch.rand(25, 3, generator=g) * 2 - 1
+    Y = torch.randn(25, 4, generator=g)
+    scales, width = torch.tensor([0.7, 1.3, 0.9]), torch.tensor([0.5, 0.25, 0.4])
+    m = make_model(X, Y, 2, variant="PLMC", kernel="rbf", decomp=[[0, 2], [1]], prior_scales=scales, prior_width=width)
+    # initialised at the prior mean (:169-176), then perturbed by make_model
+    p = oracle_params(m)
+    c0, c1 = p.components
+    ell0 = O.softplus(c0.raw_lengthscale).detach().numpy()[:, 0]
+    ell1 = O.softplus(c1.raw_lengthscale).detach().numpy()[:, 0]
+    ref0 = sum(multivariate_normal(mean=scales[[0, 2]].numpy(), cov=np.diag((scales * width)[[0, 2]].numpy())).logpdf(e)
+               for e in ell0)
+    ref1 = sum(norm(loc=float(scales[1]), scale=float(scales[1] * width[1])).logpdf(e).sum() for e in ell1)
+    assert abs(float(O.lengthscale_log_prior(c0)) - ref0) < 1e-12 * max(1.0, abs(ref0))
+    assert abs(float(O.lengthscale_log_prior(c1)) - ref1) < 1e-12 * max(1.0, abs(ref1))
+    with torch.no_grad():
+        with_prior = O.mll(p, X, Y)
+        for c in p.components:
+            c.prior_loc = None
+        without = O.mll(p, X, Y)
+    q, n = 2, X.shape[0]
+    assert abs(float(with_prior - without) - q * (ref0 + ref1) / n) < 1e-12
+    # the product's host-side prior objects give the same densities
+    for (_, module, prior, closure), ref in zip(m.named_priors(), (ref0, ref1)):
+        assert abs(float(prior.log_prob(closure(module)).sum()) - ref) < 1e-12 * max(1.0, abs(ref))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# inducing points (ExactGPModel(n_inducing_points=m), projected_lmc.py:302-303 -> gpytorch InducingPointKernel)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel,os_", [("rbf", False), ("matern52", True)])
+def test_sgpr_with_inducing_points_on_the_data_is_the_exact_gp(kernel, os_):
+    """Q = K_fu K_uu^-1 K_uf equals K when U = X: the SGPR loss, its (then vanishing) trace term and the
+    eval-mode prediction must collapse onto the exact model."""
+    X, Y, Xs, _ = synth(50, 3, 5, 2, seed=13, ns=8)
+    m = make_model(X, Y, 2, variant="PLMC", kernel=kernel, outputscales=os_, n_inducing_points=50)
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m.covar_module.inducing_points.copy_(X)
+        p = oracle_params(m)
+        a = O.mll(p, X, Y)
+        ma, va, _ = O.predict(p, X, Y, Xs)
+        p.inducing_points = None
+        b = O.mll(p, X, Y)
+        mb, vb, _ = O.predict(p, X, Y, Xs)
+    assert abs(a - b) <= 1e-9 * abs(b)
+    assert rel_err(ma, mb) < 1e-9 and rel_err(va, vb) < 1e-9
+
+
+def test_sgpr_objective_is_a_lower_bound_of_the_exact_marginal_likelihood():
+    """Titsias (2009): log N(y; 0, Q + s I) - tr(K - Q) / (2 s) <= log N(y; 0, K + s I) for any inducing set."""
+    X, Y, _, _ = synth(70, 2, 4, 2, seed=14)
+    m = make_model(X, Y, 2, variant="PLMC_fast", kernel="rbf", n_inducing_points=12)
+    with torch.no_grad():
+        p = oracle_params(m)
+        TY = O.project_data(p, Y)
+        sparse = O.latent_log_probs(p, X, TY)
+        p.inducing_points = None
+        exact = O.latent_log_probs(p, X, TY)
+    assert (sparse <= exact + 1e-9).all() and (sparse < exact - 1e-3).any()

@@ -19,9 +19,10 @@ GRAD_TOL = 1e-7
 PRED_TOL = 1e-7
 
 
-def run_case(n, d, p, q, variant, kernel, outputscales=False, ns=37, seed=0, grad_tol=GRAD_TOL, mll_tol=MLL_TOL):
+def run_case(n, d, p, q, variant, kernel, outputscales=False, ns=37, seed=0, grad_tol=GRAD_TOL, mll_tol=MLL_TOL,
+             **model_kwargs):
     X, Y, Xs, _ = synth(n, d, p, q, seed=seed, ns=ns)
-    m = make_model(X, Y, q, variant=variant, kernel=kernel, outputscales=outputscales, seed=seed)
+    m = make_model(X, Y, q, variant=variant, kernel=kernel, outputscales=outputscales, seed=seed, **model_kwargs)
     mc = cpu_copy(m)
     m = m.cuda()
     Xg, Yg = X.cuda(), Y.cuda()
@@ -78,6 +79,49 @@ def test_other_matern(kernel):
 def test_outputscales():
     m = run_case(n=140, d=4, p=6, q=2, variant="PLMC", kernel="matern52", outputscales=True)
     assert m.outputscale().shape == (2, 1)
+
+
+@pytest.mark.parametrize("kernel", ["rbf", "matern52"])
+def test_additive_decomp_kernels(kernel):
+    """handle_covar_ `decomp` (projected_lmc.py:151-167): k = sum_g o_g k_g(x[dims_g]), overlapping groups, every
+    sub-kernel with its own ARD lengthscales and outputscale per latent."""
+    m = run_case(300, 5, 6, 3, "PLMC", kernel, decomp=[[0, 1], [1, 2, 3], [4]], seed=5)
+    ls, os_ = m.lscales(), m.outputscale()
+    assert isinstance(ls, list) and [tuple(t.shape) for t in ls] == [(3, 2), (3, 3), (3,)]
+    assert tuple(os_.shape) == (3, 3)
+    assert any(name.startswith("covar_module.kernels.2.base_kernel.raw_lengthscale") for name, _ in m.named_parameters())
+
+
+def test_lengthscale_priors_enter_the_loss_and_the_gradients():
+    """prior_scales / prior_width (projected_lmc.py:135-149, :169-176): Normal / MultivariateNormal priors on the
+    lengthscales, initialised at the prior mean; their log-density (counted q times, as gpytorch does) is part of
+    the loss and of d loss / d raw_lengthscale."""
+    scales = torch.tensor([0.7, 1.3, 0.9, 1.1])
+    width = torch.tensor([0.5, 0.25, 0.4, 0.3])
+    m = run_case(260, 4, 5, 2, "PLMC_fast", "matern52", decomp=[[0, 2], [1], [3]], prior_scales=scales,
+                 prior_width=width, seed=6)
+    assert len(list(m.named_priors())) == 3
+    sd = m.state_dict()
+    assert "covar_module.kernels.0.base_kernel.lengthscale_prior.loc" in sd
+    assert "covar_module.kernels.1.base_kernel.lengthscale_prior.scale" in sd
+    m2 = run_case(260, 4, 5, 2, "PLMC", "rbf", prior_scales=scales, prior_width=width, outputscales=True, seed=7)
+    assert "covar_module.base_kernel.lengthscale_prior._unbroadcasted_scale_tril" in m2.state_dict()
+
+
+@pytest.mark.parametrize("variant,kernel,os_", [("PLMC", "matern52", False), ("PLMC_fast", "rbf", True)])
+def test_inducing_point_model(variant, kernel, os_):
+    """ExactGPModel(n_inducing_points=m) (projected_lmc.py:302-303): SGPR loss (low-rank covariance + added trace
+    term), gradients to every parameter INCLUDING the inducing points, and the eval-mode prediction with the
+    diagonal correction, against the dense oracle."""
+    m = run_case(330, 3, 6, 2, variant, kernel, outputscales=os_, n_inducing_points=40, seed=8, grad_tol=1e-6)
+    ip = dict(m.named_parameters())["covar_module.inducing_points"]
+    assert ip.grad is not None and ip.grad.abs().max().item() > 0
+    assert "covar_module.base_kernel.raw_lengthscale" in m.state_dict() or \
+        "covar_module.base_kernel.base_kernel.raw_lengthscale" in m.state_dict()
+
+
+def test_inducing_points_with_an_additive_kernel():
+    run_case(280, 4, 5, 2, "PLMC", "matern52", n_inducing_points=150, decomp=[[0, 1], [2, 3]], seed=9, grad_tol=1e-6)
 
 
 def test_ragged_sizes():

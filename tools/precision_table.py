@@ -32,7 +32,9 @@ for name, kind, n, ell in CASES:
         LatentEngine.rns_min_k, LatentEngine.rns_min_mnk = 0, 0       # residues for every routed product
         if mode == "rns":
             LatentEngine.rns_moduli, LatentEngine.rns_moduli_kinv = prec, kinv
-        mg = cpu_copy(m).cuda()
+        mg = cpu_copy(m)
+        mg._engine = LatentEngine()
+        mg = mg.cuda()
         for p in mg.parameters():
             p.grad = None
         loss = -ProjectedLMCmll(mg.likelihood, mg)(mg(X.cuda()), Y.cuda())
