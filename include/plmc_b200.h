@@ -105,6 +105,9 @@ int plmc_project_bwd(const double* Y, const double* G, long long ldg, double* dT
 /* ---- (2) Gram build: handle_covar_ kernels, projected_lmc.py:151-167, evaluated
  * at :1201; gpytorch sq_dist semantics (centre by column mean, expansion,
  * clamp_min 0), ScaleKernel and the GaussianLikelihood diagonal (:1200).       */
+/* host-only helper (HOST pointers, no device work): k(s) and dk/ds of PLMC_KERNEL_* evaluated by the same source
+ * the device kernels compile (csrc/kernel_math.cuh: hand-written exp / sqrt), for CPU-side accuracy tests. */
+int plmc_kernel_profile_host(int kernel_id, const double* s_host, long long n, double* k_host, double* dk_host);
 /* xmean[k] = mean_i X[i,k] */
 int plmc_col_mean(const double* X, long long n, int d, double* xmean, void* stream);
 /* Z[l, i, k] = (X[i,k]-xmean[k]) / ell[l,k], zero padded to [q, rows_pad, dpad];

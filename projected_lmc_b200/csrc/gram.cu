@@ -374,6 +374,22 @@ static int launch_gram(int kernel_id, dim3 grid, size_t smem, cudaStream_t st, c
 
 extern "C" {
 
+/* host only (no device work): k(s) and dk/ds of kernel `kernel_id` evaluated with the SAME source the device
+ * kernels compile (csrc/kernel_math.cuh) -- lets the CPU test-suite check the hand-written exp / sqrt. */
+int plmc_kernel_profile_host(int kernel_id, const double* s_host, long long n, double* k_host, double* dk_host) {
+    if (!s_host || !k_host || !dk_host || n < 0) return PLMC_ERR_BADARG;
+    for (long long i = 0; i < n; ++i) {
+        switch (kernel_id) {
+            case 0: kernel_value_grad<0>(s_host[i], k_host[i], dk_host[i]); break;
+            case 1: kernel_value_grad<1>(s_host[i], k_host[i], dk_host[i]); break;
+            case 2: kernel_value_grad<2>(s_host[i], k_host[i], dk_host[i]); break;
+            case 3: kernel_value_grad<3>(s_host[i], k_host[i], dk_host[i]); break;
+            default: return PLMC_ERR_BADARG;
+        }
+    }
+    return PLMC_OK;
+}
+
 int plmc_col_mean(const double* X, long long n, int d, double* xmean, void* stream) {
     if (!X || !xmean || n <= 0 || d <= 0) return PLMC_ERR_BADARG;
     col_mean_kernel<<<d, 256, 0, (cudaStream_t)stream>>>(X, n, d, xmean);
