@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--no-predict", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--test-points", type=int, default=0)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="f32: float32 model -> fp32-grade arithmetic (32-bit operands on the INT8 path, FP64 storage)")
     return ap.parse_args()
 
 
@@ -202,13 +204,14 @@ def products_per_fp64_product(eng):
     q n^3 FLOP) runs at the main precision, the explicit inverse (2/3; K^-1 feeds only the gradients) at the
     reduced one.  (main, inverse, weighted, description)"""
     mode = eng.emulation_mode() if hasattr(eng, "emulation_mode") else ("digits" if getattr(eng, "fp64_slices", 0) else "fp64")
+    f32 = getattr(eng, "grade", "fp64") == "fp32"
     if mode == "rns":
-        m = eng.rns_moduli
-        mk = min(getattr(eng, "rns_moduli_kinv", 0) or m, m)
+        m = min(eng.rns_moduli_f32, eng.rns_moduli) if f32 else eng.rns_moduli
+        mk = m if f32 else min(getattr(eng, "rns_moduli_kinv", 0) or m, m)
         return m, mk, (m + 2.0 * mk) / 3.0, f"{m} moduli in potrf, {mk} in trtri/lauum"
     if mode == "digits":
-        s = eng.fp64_slices
-        sk = min(getattr(eng, "fp64_slices_kinv", 0) or s, s)
+        s = min(eng.fp64_slices_f32, eng.fp64_slices) if f32 else eng.fp64_slices
+        sk = s if f32 else min(getattr(eng, "fp64_slices_kinv", 0) or s, s)
         a, b = s * (s + 1) // 2, sk * (sk + 1) // 2
         return a, b, (a + 2.0 * b) / 3.0, f"{s} digit planes in potrf, {sk} in trtri/lauum"
     return 0, 0, 0.0, "pure FP64"
@@ -486,6 +489,9 @@ def run_train_workload(args, cfg, world, rank, dev):
     Xh, Yh = make_data(n, cfg["d"], p_tot, q_tot, seed=0)
     Xh, Yh = Xh.pin_memory(), Yh.pin_memory()
     model = build_model(Xh.clone(), Yh.clone(), q_tot, cfg["kernel"]).to(dev)
+    if args.dtype == "f32":
+        model = model.float()
+        Xh, Yh = Xh.float().pin_memory(), Yh.float().pin_memory()
     if world > 1:
         pdist.shard_latents(model, rank, world)
     lo, hi = model._latent_range
@@ -578,14 +584,15 @@ def run_train_workload(args, cfg, world, rank, dev):
         if world > 1:
             dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
         e2e = {"value": models_per_step / (float(ms2.item()) * 1e-3), "unit": "it/s",
-               "h2d_bytes_per_step": (Xh.numel() + Yh.numel()) * 8, "d2h_bytes_per_step": 8}
+               "h2d_bytes_per_step": (Xh.numel() + Yh.numel()) * Xh.element_size(),
+               "d2h_bytes_per_step": Xh.element_size()}
 
     # ---- prediction: batched predictive mean/variance on the same model (secondary metric) -------
     predict = None
     if not args.no_predict:
         n_test = args.test_points or (8192 if not small else 4096)
         gt = torch.Generator().manual_seed(7)
-        Xs = (torch.rand(n_test, cfg["d"], generator=gt, dtype=torch.float64) * 2 - 1).to(dev)
+        Xs = (torch.rand(n_test, cfg["d"], generator=gt, dtype=torch.float64) * 2 - 1).to(dev).to(Xd.dtype)
         model.eval()
         with torch.no_grad(), warnings.catch_warnings():
             warnings.simplefilter("ignore")
@@ -624,7 +631,7 @@ def run_train_workload(args, cfg, world, rank, dev):
         line = {
             "metric": "train_iters_per_sec", "value": value, "unit": "it/s", "n_gpus": world, "steps": steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(args, cfg, world),
             "loss": float(loss.item()),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

@@ -90,6 +90,13 @@ class LatentEngine:
     # (tolerance 1e-6) and save a quarter (digits) / an eighth (rns) of those two steps; 0 = same as the main one.
     fp64_slices_kinv = int(__import__("os").environ.get("PLMC_FP64_SLICES_KINV", "6"))
     rns_moduli_kinv = int(__import__("os").environ.get("PLMC_RNS_MODULI_KINV", "14"))
+    # fp32 grade (models whose tensors are float32; the reference's GPU default, experiments.py:4-8, tolerance 1e-4):
+    # storage and accumulation stay FP64, but the operands of the large products carry 32 bits (10 moduli =
+    # 10 INT8 products, or 4 digit planes = 10 products) in the factorisation AND the inverse: a third fewer
+    # tensor operations than the fp64 grade, results ~1e-8 from the FP64 ones (far inside 1e-4)
+    grade = "fp64"
+    rns_moduli_f32 = int(__import__("os").environ.get("PLMC_RNS_MODULI_F32", "10"))
+    fp64_slices_f32 = int(__import__("os").environ.get("PLMC_FP64_SLICES_F32", "4"))
     rns_flags = int(__import__("os").environ.get("PLMC_RNS_FLAGS", "0"))
     # the residue scheme pays a fixed cost per output element: products with K < rns_min_k or M*N*K < rns_min_mnk
     # run on digit planes of the matching grade (fp64_slices / fp64_slices_kinv) instead; 0 = residues everywhere
@@ -104,7 +111,8 @@ class LatentEngine:
 
     def _configure_fp64(self, device, np_, q=1):
         mode, md = self.emulation_mode(), self.fp64_min_dim
-        key = (mode, md, self.fp64_min_mnk, self.fp64_slices, self.fp64_slices_kinv, self.rns_moduli, self.rns_moduli_kinv,
+        f32 = (self.grade == "fp32")
+        key = (mode, f32, md, self.fp64_min_mnk, self.fp64_slices, self.fp64_slices_kinv, self.rns_moduli, self.rns_moduli_kinv,
                self.rns_flags, self.rns_min_k, self.rns_min_mnk, str(device), np_, q)
         if key == self._cfg_key:
             return
@@ -133,16 +141,19 @@ class LatentEngine:
             self._oz = None
             self._oz = torch.empty((need,), dtype=torch.uint8, device=device)
         if mode == "rns":
-            mk = min(self.rns_moduli_kinv or self.rns_moduli, self.rns_moduli)
-            alt = self.fp64_slices if (self.rns_min_k > 0 or self.rns_min_mnk > 0) else 0
-            altk = min(self.fp64_slices_kinv or alt, alt)
-            self._cfg = (ops.gemm_cfg(self._oz, ops.GEMM_INT8_RNS, self.rns_moduli, md, self.rns_flags, alt,
+            mm = min(self.rns_moduli_f32, self.rns_moduli) if f32 else self.rns_moduli
+            mk = mm if f32 else min(self.rns_moduli_kinv or self.rns_moduli, self.rns_moduli)
+            sl = min(self.fp64_slices_f32, self.fp64_slices) if f32 else self.fp64_slices
+            alt = sl if (self.rns_min_k > 0 or self.rns_min_mnk > 0) else 0
+            altk = alt if f32 else min(self.fp64_slices_kinv or alt, alt)
+            self._cfg = (ops.gemm_cfg(self._oz, ops.GEMM_INT8_RNS, mm, md, self.rns_flags, alt,
                                       self.rns_min_k, self.rns_min_mnk, self.fp64_min_mnk),
                          ops.gemm_cfg(self._oz, ops.GEMM_INT8_RNS, mk, md, self.rns_flags, altk,
                                       self.rns_min_k, self.rns_min_mnk, self.fp64_min_mnk))
         else:
-            sk = min(self.fp64_slices_kinv or self.fp64_slices, self.fp64_slices)
-            self._cfg = (ops.gemm_cfg(self._oz, ops.GEMM_INT8_DIGITS, self.fp64_slices, md, min_mnk=self.fp64_min_mnk),
+            sm_ = min(self.fp64_slices_f32, self.fp64_slices) if f32 else self.fp64_slices
+            sk = sm_ if f32 else min(self.fp64_slices_kinv or self.fp64_slices, self.fp64_slices)
+            self._cfg = (ops.gemm_cfg(self._oz, ops.GEMM_INT8_DIGITS, sm_, md, min_mnk=self.fp64_min_mnk),
                          ops.gemm_cfg(self._oz, ops.GEMM_INT8_DIGITS, sk, md, min_mnk=self.fp64_min_mnk))
 
     @property

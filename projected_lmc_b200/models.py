@@ -124,7 +124,11 @@ class ExactGPModel(torch.nn.Module):
     def _apply(self, fn, *args, **kwargs):
         self.train_inputs = tuple(fn(t) for t in self.train_inputs)
         self.train_targets = fn(self.train_targets)
-        return super()._apply(fn, *args, **kwargs)
+        out = super()._apply(fn, *args, **kwargs)
+        eng = getattr(self, "_engine", None)
+        if eng is not None:      # .float() / .double(): the arithmetic grade follows the model's dtype
+            eng.grade = "fp32" if self.train_inputs[0].dtype == torch.float32 else "fp64"
+        return out
 
     def named_priors(self):
         """(name, module, prior, closure) of every registered prior (gpytorch Module.named_priors)."""
@@ -267,6 +271,7 @@ class ProjectedGPModel(ExactGPModel):
         self.eps = eps
 
         self._engine = LatentEngine()
+        self._engine.grade = "fp32" if train_x.dtype == torch.float32 else "fp64"
         self._latent_range = (0, n_latents)   # latents owned by this process (distributed.shard_latents)
         self._dist_group = None
         self._pred_cache = None

@@ -271,7 +271,7 @@ def test_eval_cache_is_invalidated_by_parameter_updates():
         assert m._pred_key != key and not torch.allclose(a, c)
 
 
-def test_float32_inputs_are_computed_in_float64():
+def test_float32_small_model_within_fp32_tolerance():
     X, Y, Xs, _ = synth(80, 2, 4, 2, ns=10)
     m = make_model(X, Y, 2, variant="PLMC_fast", kernel="rbf")
     ref = -O.mll(oracle_params(cpu_copy(m)), X, Y)
@@ -281,6 +281,35 @@ def test_float32_inputs_are_computed_in_float64():
     assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())       # north_star fp32 tolerance
     loss.backward()
     assert all(p.grad is not None and p.grad.dtype == torch.float32 for p in m32.parameters())
+
+
+def test_float32_model_runs_the_fp32_grade_on_the_tensor_path_within_1e_minus_4():
+    """dtype = float32 (the reference's GPU default, experiments.py:4-8): 32-bit operands on the INT8 path
+    (10 moduli / 4 digit planes), FP64 storage; north_star tolerance 1e-4 for MLL, gradients and predictions."""
+    X, Y, Xs, _ = synth(1500, 4, 6, 3, seed=12, ns=40)
+    m = make_model(X, Y, 3, variant="PLMC", kernel="matern52")
+    mc = cpu_copy(m)
+    ref = -O.mll(oracle_params(mc), X, Y)
+    ref.backward()
+    m32 = m.float().cuda()
+    assert m32._engine.grade == "fp32"
+    loss = -ProjectedLMCmll(m32.likelihood, m32)(m32(X.float().cuda()), Y.float().cuda())
+    loss.backward()
+    cfg = m32._engine.cfg_main
+    assert cfg is not None and cfg.precision == m32._engine.rns_moduli_f32 and m32._engine.cfg_kinv.precision == cfg.precision
+    assert abs(loss.item() - ref.item()) <= 1e-4 * abs(ref.item())
+    refg = dict(mc.named_parameters())
+    for name, prm in m32.named_parameters():
+        if refg[name].grad is not None:
+            assert rel_err(prm.grad, refg[name].grad) <= 1e-4, name
+    m32.eval()
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pred = m32.full_likelihood()(m32(Xs.float().cuda()))
+        mean_ref, _, var_ref = O.predict(oracle_params(mc), X, Y, Xs)
+    assert pred.mean.dtype == torch.float32
+    assert rel_err(pred.mean, mean_ref) <= 1e-4 and rel_err(pred.variance, var_ref) <= 1e-4
+    assert m32.double()._engine.grade == "fp64"
 
 
 def test_not_psd_error_after_max_tries():
