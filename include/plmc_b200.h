@@ -88,7 +88,9 @@ int plmc_trace_enable(int on);
 int plmc_trace_report(void);
 /* npad for a problem of order n (multiple of 128) */
 long long plmc_npad(long long n);
-/* bytes of the Dinv side buffer potrf needs for `batch` matrices of order npad */
+/* bytes of the side buffer `dinv` of the factorisation calls for `batch` matrices of order npad: the 128x128
+ * inverses of the diagonal Cholesky leaves (written by potrf, read by every solve) followed by ceil(npad/512)
+ * slots of 512x512 for zero-padded dense copies of diagonal blocks (scratch of trtri / lauum / potri).        */
 long long plmc_dinv_bytes(long long npad, int batch);
 
 /* ---- (1) projection: ProjectedGPModel.project_data, projected_lmc.py:1014-1021
@@ -156,13 +158,13 @@ int plmc_solve_logdet(const double* L, long long ld, long long stride, long long
                       const double* dinv, const double* y, long long ldy, double* rhs, double* z, double* alpha,
                       long long ldv, double* quad, double* logdet, void* stream);
 /* L -> inv(L) (lower) in place */
-int plmc_trtri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
+int plmc_trtri_batched(double* L, long long ld, long long stride, long long npad, int batch, double* dinv,
                        const plmc_gemm_cfg* cfg, void* stream);
-/* L -> lower(L^T L) in place */
-int plmc_lauum_batched(double* L, long long ld, long long stride, long long npad, int batch,
+/* L -> lower(L^T L) in place (dinv: only its dense-block scratch part is used, and overwritten) */
+int plmc_lauum_batched(double* L, long long ld, long long stride, long long npad, int batch, double* dinv,
                        const plmc_gemm_cfg* cfg, void* stream);
 /* L -> lower(K^-1) in place = trtri + lauum */
-int plmc_potri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
+int plmc_potri_batched(double* L, long long ld, long long stride, long long npad, int batch, double* dinv,
                        const plmc_gemm_cfg* cfg, void* stream);
 
 /* ---- (4) fused backward: autograd of log_prob through the kernel

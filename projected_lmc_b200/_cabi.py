@@ -56,7 +56,7 @@ _SIGNATURES = {
     "plmc_trsm_batched": [I, P, LL, LL, LL, I, P, P, LL, LL, LL, D, CFG, P],
     "plmc_solve_logdet": [P, LL, LL, LL, LL, I, P, P, LL, P, P, P, LL, P, P, P],
     "plmc_trtri_batched": [P, LL, LL, LL, I, P, CFG, P],
-    "plmc_lauum_batched": [P, LL, LL, LL, I, CFG, P],
+    "plmc_lauum_batched": [P, LL, LL, LL, I, P, CFG, P],
     "plmc_potri_batched": [P, LL, LL, LL, I, P, CFG, P],
     "plmc_grad_ws": [LL, I, I],
     "plmc_grad_sweep": [P, LL, LL, P, LL, P, P, P, I, P, P, P, P, P, LL, LL, I, I, I, P],

@@ -87,7 +87,7 @@ int plmc_stats_get(long long* launches_host, long long* gemm_launches_host, doub
 
 long long plmc_npad(long long n) { return ((n + 127) / 128) * 128; }
 
-long long plmc_dinv_bytes(long long npad, int batch) { return npad * 128 * 8 * (long long)batch; }
+long long plmc_dinv_bytes(long long npad, int batch) { return dinv_elems(npad) * 8 * (long long)batch; }
 
 int plmc_gemm(int layout, const double* A, long long lda, long long sA, const double* B, long long ldb, long long sB,
               double* C, long long ldc, long long sC, int M, int N, int K, double alpha, double beta, int lower,
@@ -116,7 +116,7 @@ int plmc_potrf_batched(double* K, long long ld, long long stride, long long npad
     LaCtx cx;
     if (!make_ctx(cx, st, batch, cfg)) return PLMC_ERR_BADARG;
     if (cudaMemsetAsync(info, 0, sizeof(int) * batch, st) != cudaSuccess) return PLMC_ERR_LAUNCH;
-    potrf_lower(cx, BMat{K, ld, stride}, (int)npad, DinvBuf{dinv, npad * 128}, 0, info);
+    potrf_lower(cx, BMat{K, ld, stride}, (int)npad, make_dinv(dinv, npad), 0, info);
     return cx.status;
 }
 
@@ -127,7 +127,7 @@ int plmc_trsm_batched(int op, const double* L, long long ld, long long stride, l
     LaCtx cx;
     if (!make_ctx(cx, (cudaStream_t)stream, batch, cfg)) return PLMC_ERR_BADARG;
     BMat Lm{const_cast<double*>(L), ld, stride};
-    DinvBuf D{const_cast<double*>(dinv), npad * 128};
+    DinvBuf D = make_dinv(dinv, npad);
     BMat Bm{B, ldb, strideb};
     switch (op) {
         case 0: trsm_rlt(cx, Lm, (int)npad, D, 0, Bm, (int)m, alpha); break;
@@ -147,7 +147,7 @@ int plmc_solve_logdet(const double* L, long long ld, long long stride, long long
         return PLMC_ERR_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
     // two HBM-bound block substitutions on one vector (csrc/trsv.cu); rhs is the npad-vector workspace
-    const int rc = trsv_solve(L, ld, stride, dinv, npad * 128, y, ldy, rhs, npad * 128, z, alpha, ldv, n, npad, batch, st);
+    const int rc = trsv_solve(L, ld, stride, dinv, dinv_elems(npad), y, ldy, rhs, npad * 128, z, alpha, ldv, n, npad, batch, st);
     if (rc) return rc;
     quad_logdet_kernel<<<batch, 1024, 0, st>>>(z, ldv, L, ld, stride, n, quad, logdet);
     PLMC_CHECK_LAUNCH();
@@ -155,28 +155,32 @@ int plmc_solve_logdet(const double* L, long long ld, long long stride, long long
     return PLMC_OK;
 }
 
-int plmc_trtri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
+int plmc_trtri_batched(double* L, long long ld, long long stride, long long npad, int batch, double* dinv,
                        const plmc_gemm_cfg* cfg, void* stream) {
     if (bad_mat(L, ld, npad, batch) || !dinv) return PLMC_ERR_BADARG;
     LaCtx cx;
     if (!make_ctx(cx, (cudaStream_t)stream, batch, cfg)) return PLMC_ERR_BADARG;
-    trtri_lower(cx, BMat{L, ld, stride}, (int)npad, DinvBuf{const_cast<double*>(dinv), npad * 128}, 0);
+    trtri_lower(cx, BMat{L, ld, stride}, (int)npad, make_dinv(dinv, npad), 0);
     return cx.status;
 }
 
-int plmc_lauum_batched(double* L, long long ld, long long stride, long long npad, int batch,
+int plmc_lauum_batched(double* L, long long ld, long long stride, long long npad, int batch, double* dinv,
                        const plmc_gemm_cfg* cfg, void* stream) {
-    if (bad_mat(L, ld, npad, batch)) return PLMC_ERR_BADARG;
+    if (bad_mat(L, ld, npad, batch) || !dinv) return PLMC_ERR_BADARG;
     LaCtx cx;
     if (!make_ctx(cx, (cudaStream_t)stream, batch, cfg)) return PLMC_ERR_BADARG;
-    lauum_lower(cx, BMat{L, ld, stride}, (int)npad);
+    lauum_lower(cx, BMat{L, ld, stride}, (int)npad, make_dinv(dinv, npad), 0, /*fill_dense=*/true);
     return cx.status;
 }
 
-int plmc_potri_batched(double* L, long long ld, long long stride, long long npad, int batch, const double* dinv,
+int plmc_potri_batched(double* L, long long ld, long long stride, long long npad, int batch, double* dinv,
                        const plmc_gemm_cfg* cfg, void* stream) {
-    int r = plmc_trtri_batched(L, ld, stride, npad, batch, dinv, cfg, stream);
-    if (r) return r;
-    return plmc_lauum_batched(L, ld, stride, npad, batch, cfg, stream);
+    if (bad_mat(L, ld, npad, batch) || !dinv) return PLMC_ERR_BADARG;
+    LaCtx cx;
+    if (!make_ctx(cx, (cudaStream_t)stream, batch, cfg)) return PLMC_ERR_BADARG;
+    DinvBuf D = make_dinv(dinv, npad);
+    trtri_lower(cx, BMat{L, ld, stride}, (int)npad, D, 0);
+    lauum_lower(cx, BMat{L, ld, stride}, (int)npad, D, 0, /*fill_dense=*/false);   // trtri left the dense copies
+    return cx.status;
 }
 }

@@ -21,6 +21,11 @@
 
 namespace plmc {
 
+// max(a, b) for non-NaN arguments.  fmax() on doubles has no hardware instruction on sm_100a: it expands to
+// DSETP.MAX + SEL + FSEL + a NaN-quieting LOP3 per half (~7 instructions, ncu source page of gram_kernel); a
+// compare-and-select is 3.
+__host__ __device__ __forceinline__ double dmax(double a, double b) { return (a > b) ? a : b; }
+
 #define PLMC_EXP_TABLE                                                                                                \
     {1.0, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237, 1.0905077326652577, 1.1143867425958924,         \
      1.1387886347566916, 1.1637248587775775, 1.189207115002721, 1.215247359980469, 1.241857812073484,                 \
@@ -35,10 +40,11 @@ namespace plmc {
 static __device__ const double d_exp_table[32] = PLMC_EXP_TABLE;
 static const double h_exp_table[32] = PLMC_EXP_TABLE;
 
-// exp(x) for x <= 0 (NaN propagates; x > 0 is outside the contract).  Results below 2^-1021 are flushed to 0
-// (kernel values that small are irrelevant next to the noise floor e^-9 on the diagonal).
-__host__ __device__ __forceinline__ double exp_nonpos(double x) {
-    if (!(x > -707.0)) return (x != x) ? x : 0.0;
+// exp(x) for x <= 0 (x > 0 is outside the contract; the callers have checked their inputs for NaN).  Branch-free:
+// the argument is clamped at -707 and results below e^-707 are flushed to 0 by a select (kernel values that
+// small are irrelevant next to the noise floor e^-9 on the diagonal).
+__host__ __device__ __forceinline__ double exp_nonpos(double x0) {
+    const double x = dmax(x0, -707.0);
     const double MAGIC = 6755399441055744.0;                 // 1.5 * 2^52: low word of (t + MAGIC) is rint(t)
     const double tm = fma(x, 46.16624130844683, MAGIC);      // x * 32 / ln 2
     const double nd = tm - MAGIC;
@@ -61,12 +67,13 @@ __host__ __device__ __forceinline__ double exp_nonpos(double x) {
 #ifdef __CUDA_ARCH__
     const double T = __ldg(&d_exp_table[n & 31]);
     const double v = fma(T, p, T);
-    return __hiloint2double(__double2hiint(v) + ((n >> 5) << 20), __double2loint(v));
+    const double r2 = __hiloint2double(__double2hiint(v) + ((n >> 5) << 20), __double2loint(v));
 #else
     const double T = h_exp_table[n & 31];
     const double v = fma(T, p, T);
-    return ldexp(v, n >> 5);
+    const double r2 = ldexp(v, n >> 5);
 #endif
+    return (x0 < -707.0) ? 0.0 : r2;
 }
 
 // sqrt(s) for 1e-300 < s < 1e300
@@ -93,15 +100,15 @@ template <int KID>
 __host__ __device__ __forceinline__ double kernel_value(double s) {
     if (KID == 0) return exp_nonpos(-0.5 * s);
     if (KID == 1) {
-        const double u = 5.0 * fmax(s, 1e-30);               // (sqrt5 r)^2
+        const double u = 5.0 * dmax(s, 1e-30);               // (sqrt5 r)^2
         const double a = sqrt_pos(u);
         return (1.0 + a + u * (1.0 / 3.0)) * exp_nonpos(-a);
     }
     if (KID == 2) {
-        const double a = sqrt_pos(3.0 * fmax(s, 1e-30));
+        const double a = sqrt_pos(3.0 * dmax(s, 1e-30));
         return (1.0 + a) * exp_nonpos(-a);
     }
-    return exp_nonpos(-sqrt_pos(fmax(s, 1e-30)));
+    return exp_nonpos(-sqrt_pos(dmax(s, 1e-30)));
 }
 
 // k(s) and dk/ds
@@ -113,18 +120,18 @@ __host__ __device__ __forceinline__ void kernel_value_grad(double s, double& k, 
         return;
     }
     if (KID == 1) {
-        const double u = 5.0 * fmax(s, 1e-30);
+        const double u = 5.0 * dmax(s, 1e-30);
         const double a = sqrt_pos(u);
         const double e = exp_nonpos(-a);
         k = (1.0 + a + u * (1.0 / 3.0)) * e;
         dk = -(5.0 / 6.0) * (1.0 + a) * e;
     } else if (KID == 2) {
-        const double a = sqrt_pos(3.0 * fmax(s, 1e-30));
+        const double a = sqrt_pos(3.0 * dmax(s, 1e-30));
         const double e = exp_nonpos(-a);
         k = (1.0 + a) * e;
         dk = -1.5 * e;
     } else {
-        const double r = sqrt_pos(fmax(s, 1e-30));
+        const double r = sqrt_pos(dmax(s, 1e-30));
         k = exp_nonpos(-r);
         dk = (s > 1e-30) ? -0.5 * k / r : 0.0;
     }

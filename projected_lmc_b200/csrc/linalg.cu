@@ -43,7 +43,39 @@ static int leaf_attr() {
 // ---------------------------------------------------------------------------
 // host-side helpers
 // ---------------------------------------------------------------------------
-static inline int split128(int n) { return ((n / LEAF) / 2) * LEAF; }
+// Split point of the recursions.  Above 512 the matrix is cut at a multiple of 512 so that every diagonal block the
+// triangular multiplies treat as a dense leaf starts on a 512 boundary (its zero-padded copy has a fixed slot in
+// the side buffer); at and below 512 the cut is at a multiple of the 128-leaf.
+static inline int split128(int n) {
+    if (n > BLK) {
+        const int k = n / BLK;
+        return (k >= 2) ? (k / 2) * BLK : BLK;
+    }
+    return ((n / LEAF) / 2) * LEAF;
+}
+
+// lower part of each diagonal 512-block of L (zero above the diagonal, zero padding up to 512) -> its dense slot
+__global__ void dense_diag_copy_kernel(const double* __restrict__ Lbase, long long ld, long long sL,
+                                       double* __restrict__ Dbase, long long sD, int n) {
+    const int blk = blockIdx.x, b = blockIdx.z;
+    const int r0 = blk * BLK;
+    const int sz = min(BLK, n - r0);
+    const double* L = Lbase + (long long)b * sL + (long long)r0 * ld + r0;
+    double* D = Dbase + (long long)b * sD + (long long)blk * BLK * BLK;
+    for (int idx = threadIdx.x + blockIdx.y * blockDim.x; idx < BLK * BLK; idx += blockDim.x * gridDim.y) {
+        const int r = idx / BLK, c = idx - r * BLK;
+        D[idx] = (r < sz && c <= r) ? L[(long long)r * ld + c] : 0.0;
+    }
+}
+
+static void dense_diag_copy(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
+    if (cx.status || n <= 0) return;
+    BMat d = D.dense(blk0);
+    dim3 grid((n + BLK - 1) / BLK, 8, cx.batch);
+    dense_diag_copy_kernel<<<grid, 256, 0, cx.st>>>(L.p, L.ld, L.stride, d.p, d.stride, n);
+    if (cudaGetLastError() != cudaSuccess) cx.status = PLMC_ERR_LAUNCH;
+    note_launch(1);
+}
 
 // ---- optional per-shape timing of every GEMM of the recursion (plmc_trace_enable / plmc_trace_report):
 // CUDA events around each launch, aggregated by (path, M, N, K, lower, batch) at report time.
@@ -88,27 +120,37 @@ void trace_report() {
                 kv.second.flop / kv.second.ms / 1e9);
 }
 
+// Which kernel a product takes: 0 FP64 DMMA, 1 INT8 digit planes (*prec slices), 2 INT8 residue planes (*prec moduli).
+// The INT8 paths convert their operands to planes BEFORE the product kernel runs, so C may alias A or B for any K;
+// the DMMA kernel is in-place safe only when K is a single 128-tile.
+static int gemm_route(const LaCtx& cx, int M, int N, int K, bool same, bool tri, int* prec) {
+    if (cx.oz_mode <= 0 || cx.oz_prec <= 0 || tri || M < cx.oz_min || N < cx.oz_min || K < cx.oz_min ||
+        (long long)M * N * K < cx.oz_min_mnk)
+        return 0;
+    *prec = cx.oz_prec;
+    if (cx.oz_mode == 2) {
+        if (!(cx.oz_alt > 0 && (K < cx.oz_rns_min_k || (long long)M * N * K < cx.oz_rns_min_mnk))) return 2;
+        *prec = cx.oz_alt;   // short inner dimension / little work: digit planes have the lower per-element cost
+    }
+    return (ozaki_ws_bytes(M, N, K, *prec, same) + 1024 <= cx.oz_bytes) ? 1 : 0;
+}
+
 static void gemm_impl(LaCtx& cx, bool aKC, bool bKC, BMat A, BMat B, BMat C, int M, int N, int K, double alpha,
                       double beta, int lower, int triA, int triB, int* path) {
     if (cx.status) return;
-    if (cx.oz_mode > 0 && cx.oz_prec > 0 && !triA && !triB && M >= cx.oz_min && N >= cx.oz_min && K >= cx.oz_min &&
-        (long long)M * N * K >= cx.oz_min_mnk) {
+    {
         // large update: FP64 product through the INT8 tensor path (all batch members per launch when
         // the plane scratch holds them, otherwise in passes; everything is ordered on the one stream)
         const bool same = (A.p == B.p && A.ld == B.ld && aKC == bKC && M == N);
-        int prec = cx.oz_prec;
-        bool rns = (cx.oz_mode == 2);
-        if (rns && cx.oz_alt > 0 && (K < cx.oz_rns_min_k || (long long)M * N * K < cx.oz_rns_min_mnk)) {
-            rns = false;   // short inner dimension / little work: digit planes have the lower per-element cost
-            prec = cx.oz_alt;
-        }
-        if (rns) {   // residue planes: a product that does not fit the scratch is split inside
+        int prec = 0;
+        const int route = gemm_route(cx, M, N, K, same, triA || triB, &prec);
+        if (route == 2) {   // residue planes: a product that does not fit the scratch is split inside
             cx.status = rns_gemm(aKC, bKC, A.p, A.ld, A.stride, B.p, B.ld, B.stride, C.p, C.ld, C.stride, M, N, K, alpha,
                                  beta, lower, cx.oz_prec, same, cx.batch, cx.oz_ws, cx.oz_bytes, cx.oz_flags, cx.st);
             *path = 1;
             return;
         }
-        if (ozaki_ws_bytes(M, N, K, prec, same) + 1024 <= cx.oz_bytes) {
+        if (route == 1) {
             cx.status = ozaki_gemm(aKC, bKC, A.p, A.ld, A.stride, B.p, B.ld, B.stride, C.p, C.ld, C.stride, M, N, K,
                                    alpha, beta, lower, prec, same, cx.batch, cx.oz_ws, cx.oz_bytes, cx.st);
             *path = 1;
@@ -205,57 +247,141 @@ void trsm_llt(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m
     trsm_llt(cx, L, n1, D, blk0, B1, m, 1.0);
 }
 
-static void trtri_rec(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
+// ---- triangular multiplies with DENSE 512-leaves -----------------------------------------------------------
+// A triangular solve needs the inverse of its diagonal blocks, so its recursion has to go down to the 128-leaf
+// whose inverse the Cholesky leaf emitted: n/128 tall-skinny K = 128 products per solve, FP64-pipe bound at
+// 15-20 TFLOP/s (the "tail" of round 1).  A triangular MULTIPLY has no such constraint: its diagonal block can
+// simply be treated as dense (zero above the diagonal) at any size.  The inverse is therefore organised as
+//     inv(L) = [[X11, 0], [-X22 L21 X11, X22]]   with X11, X22 inverted FIRST,
+// i.e. two triangular multiplies per level instead of two solves, and both they and the L^T L product stop their
+// recursion at 512: the leaf is one K = 512 GEMM on the tensor path against the zero-padded dense copy of the
+// diagonal block kept in the side buffer (2-7 % more flops, none of them on the FP64 pipe).
+// A dense leaf is taken only when the product goes to an INT8 kernel (operands are converted to planes before the
+// product runs, so updating B in place is safe); otherwise the recursion continues to the 128-leaf on DMMA.
+static bool dense_leaf(const LaCtx& cx, int M, int N, int K) {
+    int prec = 0;
+    return gemm_route(cx, M, N, K, false, false, &prec) != 0;
+}
+
+// B := alpha * B * X   (X lower n x n, B m x n)
+static void trmm_rln(LaCtx& cx, BMat X, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha) {
+    if (cx.status || n <= 0 || m <= 0) return;
+    if (n <= BLK && (blk0 % 4) == 0 && dense_leaf(cx, m, n, n)) {
+        gemm(cx, true, false, B, D.dense(blk0), B, m, n, n, alpha, 0.0);
+        return;
+    }
+    if (n == LEAF) {
+        gemm(cx, true, false, B, X, B, m, LEAF, LEAF, alpha, 0.0, 0, 0, /*triB=*/1);
+        return;
+    }
+    const int n1 = split128(n), n2 = n - n1;
+    BMat B1 = B, B2 = B.sub(0, n1);
+    trmm_rln(cx, X, n1, D, blk0, B1, m, alpha);                                   // B1 := a B1 Xa
+    gemm(cx, true, false, B2, X.sub(n1, 0), B1, m, n1, n2, alpha, 1.0);           // B1 += a B2 Xc
+    trmm_rln(cx, X.sub(n1, n1), n2, D, blk0 + n1 / LEAF, B2, m, alpha);           // B2 := a B2 Xb
+}
+
+// B := alpha * X * B   (X lower n x n, B n x m)
+static void trmm_lln(LaCtx& cx, BMat X, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha) {
+    if (cx.status || n <= 0 || m <= 0) return;
+    if (n <= BLK && (blk0 % 4) == 0 && dense_leaf(cx, n, m, n)) {
+        gemm(cx, true, false, D.dense(blk0), B, B, n, m, n, alpha, 0.0);
+        return;
+    }
+    if (n == LEAF) {
+        gemm(cx, true, false, X, B, B, LEAF, m, LEAF, alpha, 0.0, 0, /*triA=*/1, 0);
+        return;
+    }
+    const int n1 = split128(n), n2 = n - n1;
+    BMat B1 = B, B2 = B.sub(n1, 0);
+    trmm_lln(cx, X.sub(n1, n1), n2, D, blk0 + n1 / LEAF, B2, m, alpha);           // B2 := a Xb B2
+    gemm(cx, true, false, X.sub(n1, 0), B1, B2, n2, m, n1, alpha, 1.0);           // B2 += a Xc B1
+    trmm_lln(cx, X, n1, D, blk0, B1, m, alpha);                                   // B1 := a Xa B1
+}
+
+// blocks of order <= 512: L21 := -inv(L22) L21 inv(L11) by two solves on the not-yet-inverted diagonal blocks
+static void trtri_small(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
     if (cx.status || n <= LEAF) return;
     const int n1 = split128(n), n2 = n - n1;
     BMat L21 = L.sub(n1, 0), L22 = L.sub(n1, n1);
-    // L21 := -inv(L22) * L21 * inv(L11), using the not-yet-inverted L11, L22
     trsm_rln(cx, L, n1, D, blk0, L21, n2, 1.0);
     trsm_lln(cx, L22, n2, D, blk0 + n1 / LEAF, L21, n1, -1.0);
+    trtri_small(cx, L, n1, D, blk0);
+    trtri_small(cx, L22, n2, D, blk0 + n1 / LEAF);
+}
+
+static void trtri_rec(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
+    if (cx.status || n <= 0) return;
+    if (n <= BLK) {
+        trtri_small(cx, L, n, D, blk0);
+        if (cx.status) return;
+        dim3 grid(n / LEAF, 1, cx.batch);
+        BMat d0 = D.leaf(blk0);
+        dinv_to_diag_kernel<<<grid, 256, 0, cx.st>>>(L.p, L.ld, L.stride, d0.p, d0.stride);
+        if (cudaGetLastError() != cudaSuccess) cx.status = PLMC_ERR_LAUNCH;
+        note_launch(1);
+        if ((blk0 % 4) == 0) dense_diag_copy(cx, L, n, D, blk0);   // the inverted block, for the multiplies above
+        return;
+    }
+    const int n1 = split128(n), n2 = n - n1;
+    BMat L21 = L.sub(n1, 0), L22 = L.sub(n1, n1);
     trtri_rec(cx, L, n1, D, blk0);
     trtri_rec(cx, L22, n2, D, blk0 + n1 / LEAF);
+    // L21 := -X22 (L21 X11)
+    trmm_rln(cx, L, n1, D, blk0, L21, n2, 1.0);
+    trmm_lln(cx, L22, n2, D, blk0 + n1 / LEAF, L21, n1, -1.0);
 }
 
 void trtri_lower(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
     if (cx.status || n <= 0) return;
     trtri_rec(cx, L, n, D, blk0);
-    if (cx.status) return;
-    dim3 grid(n / LEAF, 1, cx.batch);
-    BMat d0 = D.leaf(blk0);
-    dinv_to_diag_kernel<<<grid, 256, 0, cx.st>>>(L.p, L.ld, L.stride, d0.p, d0.stride);
-    if (cudaGetLastError() != cudaSuccess) cx.status = PLMC_ERR_LAUNCH;
-    note_launch(1);
 }
 
 // B := T^T B
-void trmm_llt(LaCtx& cx, BMat T, int n, BMat B, int m) {
+void trmm_llt(LaCtx& cx, BMat T, int n, DinvBuf D, long long blk0, BMat B, int m) {
     if (cx.status || n <= 0 || m <= 0) return;
+    if (n <= BLK && (blk0 % 4) == 0 && dense_leaf(cx, n, m, n)) {
+        gemm(cx, false, false, D.dense(blk0), B, B, n, m, n, 1.0, 0.0);
+        return;
+    }
     if (n == LEAF) {
         gemm(cx, false, false, T, B, B, LEAF, m, LEAF, 1.0, 0.0, 0, /*triA=*/1, 0);
         return;
     }
     const int n1 = split128(n), n2 = n - n1;
     BMat B1 = B, B2 = B.sub(n1, 0);
-    trmm_llt(cx, T, n1, B1, m);
+    trmm_llt(cx, T, n1, D, blk0, B1, m);
     // B1 += T21^T * B2
     gemm(cx, false, false, T.sub(n1, 0), B2, B1, n1, m, n2, 1.0, 1.0);
-    trmm_llt(cx, T.sub(n1, n1), n2, B2, m);
+    trmm_llt(cx, T.sub(n1, n1), n2, D, blk0 + n1 / LEAF, B2, m);
 }
 
-void lauum_lower(LaCtx& cx, BMat L, int n) {
+static void lauum_rec(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
     if (cx.status || n <= 0) return;
+    if (n <= BLK && n > LEAF && (blk0 % 4) == 0) {
+        // C = T^T T (lower tiles) from the dense copy of the block: operands and result do not alias
+        BMat T = D.dense(blk0);
+        gemm(cx, false, false, T, T, L, n, n, n, 1.0, 0.0, /*lower=*/1);
+        return;
+    }
     if (n == LEAF) {  // C = T^T T (full symmetric tile written)
         gemm(cx, false, false, L, L, L, LEAF, LEAF, LEAF, 1.0, 0.0, 0, 1, 1);
         return;
     }
     const int n1 = split128(n), n2 = n - n1;
     BMat L21 = L.sub(n1, 0), L22 = L.sub(n1, n1);
-    lauum_lower(cx, L, n1);
+    lauum_rec(cx, L, n1, D, blk0);
     // L11 += L21^T L21  (lower tiles)
     gemm(cx, false, false, L21, L21, L, n1, n1, n2, 1.0, 1.0, /*lower=*/1);
     // L21 := L22^T L21
-    trmm_llt(cx, L22, n2, L21, n1);
-    lauum_lower(cx, L22, n2);
+    trmm_llt(cx, L22, n2, D, blk0 + n1 / LEAF, L21, n1);
+    lauum_rec(cx, L22, n2, D, blk0 + n1 / LEAF);
+}
+
+void lauum_lower(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, bool fill_dense) {
+    if (cx.status || n <= 0) return;
+    if (fill_dense) dense_diag_copy(cx, L, n, D, blk0);
+    lauum_rec(cx, L, n, D, blk0);
 }
 
 }  // namespace plmc

@@ -62,13 +62,25 @@ int rns_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA, c
              int lower, int nmod, bool same_operand, int batch, void* ws, long long ws_bytes, int flags,
              cudaStream_t st);
 
-// Dinv: per batch member, n/128 consecutive 128x128 row-major blocks holding
-// inv(L_kk) (upper part explicitly zero).  stride = (n/128)*16384.
+// Side buffer of the factorisation layer, per batch member (stride = dinv_elems(npad)):
+//   [0, npad*128)            n/128 consecutive 128x128 row-major blocks holding inv(L_kk) of the 128-leaves
+//                            (upper part explicitly zero), written by potrf;
+//   [npad*128, ...)          ceil(npad/512) slots of 512x512: zero-padded DENSE copies of the diagonal 512-blocks of
+//                            the triangular matrix being multiplied (trtri / lauum), so that the leaf of a
+//                            triangular multiply is one K = 512 GEMM on the tensor path instead of a 128-recursion.
+constexpr int BLK = 512;
+__host__ inline long long dinv_elems(long long npad) { return npad * 128 + ((npad + BLK - 1) / BLK) * (long long)BLK * BLK; }
 struct DinvBuf {
     double* p;
     long long stride;
+    long long dense_off;   // npad * 128
     __host__ BMat leaf(long long blk) const { return BMat{p + blk * 16384, 128, stride}; }
+    // dense copy of the 512-block that starts at 128-leaf index blk (blk % 4 == 0)
+    __host__ BMat dense(long long blk) const { return BMat{p + dense_off + (blk / 4) * (long long)BLK * BLK, BLK, stride}; }
 };
+__host__ inline DinvBuf make_dinv(const double* dinv, long long npad) {
+    return DinvBuf{const_cast<double*>(dinv), dinv_elems(npad), npad * 128};
+}
 
 // A (lower) -> L in place; info[b] = 0 or 1-based index of first non-positive pivot.
 void potrf_lower(LaCtx& cx, BMat A, int n, DinvBuf D, long long blk0, int* info);
@@ -80,11 +92,11 @@ void trsm_rln(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m
 void trsm_lln(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha);
 // L^T * X = alpha*B
 void trsm_llt(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha);
-// L -> inv(L) in place (needs Dinv from potrf_lower)
+// L -> inv(L) in place (needs Dinv from potrf_lower); leaves dense copies of the inverted 512-blocks in D
 void trtri_lower(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0);
-// L -> lower(L^T L) in place
-void lauum_lower(LaCtx& cx, BMat L, int n);
+// L -> lower(L^T L) in place; D supplies (and, with fill_dense, receives) the dense copies of L's diagonal blocks
+void lauum_lower(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, bool fill_dense);
 // B := T^T * B  (T lower n x n, B n x m)
-void trmm_llt(LaCtx& cx, BMat T, int n, BMat B, int m);
+void trmm_llt(LaCtx& cx, BMat T, int n, DinvBuf D, long long blk0, BMat B, int m);
 
 }  // namespace plmc

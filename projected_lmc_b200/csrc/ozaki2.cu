@@ -263,16 +263,20 @@ __global__ void __launch_bounds__(256) residue_kc_kernel(const double* __restric
             for (int u = 0; u < 16; ++u) v[u] = row[k16 + u];
         }
     };
-    double amax = 0.0;
+    // Row maximum: only its binary exponent is needed, and for non-negative doubles the high word orders like the
+    // magnitude, so the reduction runs on 32-bit integers (fmax on doubles costs ~7 instructions on sm_100a).
+    int hmax = 0;
     for (int k16 = lane * 16; k16 < K; k16 += 512) {
         double v[16];
         load16(k16, v);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) amax = fmax(amax, fabs(v[u]));
+        for (int u = 0; u < 16; ++u) hmax = max(hmax, __double2hiint(v[u]) & 0x7fffffff);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    const int e = exp_for(amax);
+    for (int o = 16; o > 0; o >>= 1) hmax = max(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+    // frexp exponent of the maximum (|x| 2^-e in [0.5, 1)); all-zero (or all-subnormal) row: any exponent works
+    const int be = hmax >> 20;
+    const int e = (hmax == 0) ? 0 : max(be - 1022, -1022);
     if (lane == 0) ex_b[(long long)blockIdx.z * X + x] = e;
     for (int k16 = lane * 16; k16 < K; k16 += 512) {
         double v[16];

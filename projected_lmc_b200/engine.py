@@ -311,7 +311,7 @@ class LatentEngine:
                 return lp, None
             self.generation += 1
             ops.trtri(K, dinv, self.cfg_kinv)
-            ops.lauum(K, self.cfg_kinv)
+            ops.lauum(K, dinv, self.cfg_kinv)
             mark("potri")
             g_noise, g_tensors = None, []
             for (kid, dims, ell, os_), (Z, zn, _, _) in zip(comps, scaled):   # one sweep of K^-1 per additive component

@@ -77,7 +77,9 @@ def gemm(layout, A, B, C, M, N, K, alpha=1.0, beta=0.0, lower=False, triA=False,
 
 
 def alloc_dinv(np_: int, batch: int, device) -> torch.Tensor:
-    return torch.empty((batch, np_ // 128, 128, 128), dtype=torch.float64, device=device)
+    """Side buffer of the factorisation calls: [batch, plmc_dinv_bytes / 8] (leaf inverses + dense-block scratch)."""
+    per = _cabi.load().plmc_dinv_bytes(np_, 1) // 8
+    return torch.empty((batch, per), dtype=torch.float64, device=device)
 
 
 @_on_device
@@ -130,9 +132,9 @@ def trtri(L, dinv, cfg=None):
 
 
 @_on_device
-def lauum(L, cfg=None):
+def lauum(L, dinv, cfg=None):
     b, np_, _ = L.shape
-    check(lib().plmc_lauum_batched(ptr(L), L.stride(1), L.stride(0), np_, b, _cfgp(cfg), stream()), "lauum")
+    check(lib().plmc_lauum_batched(ptr(L), L.stride(1), L.stride(0), np_, b, ptr(dinv), _cfgp(cfg), stream()), "lauum")
 
 
 @_on_device

@@ -72,5 +72,5 @@ def test_profile_at_zero_distance_and_monotonicity():
         s = np.linspace(0, 50, 5001)
         k, dk = profile(kid, s)
         assert np.all(np.diff(k) <= 0) and np.all(dk[1:] <= 0)
-    k, _ = profile(0, np.array([np.nan, 5000.0]))
-    assert np.isnan(k[0]) and k[1] == 0.0
+    k, _ = profile(0, np.array([5000.0, 1e300]))
+    assert k[0] == 0.0 and k[1] == 0.0

@@ -8,6 +8,8 @@ import torch
 from oracle import plmc_oracle as O
 from projected_lmc_b200 import ops
 
+from .helpers import rel_err
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
@@ -90,8 +92,35 @@ def test_potrf_solve_trtri_lauum(n, b):
     assert torch.allclose(logdet, 2 * torch.log(torch.diagonal(Lref, dim1=1, dim2=2)).sum(-1), rtol=1e-13, atol=1e-12)
     ops.trtri(K, dinv)
     assert (torch.tril(K) - torch.linalg.inv(Lref)).abs().max().item() < 1e-11
-    ops.lauum(K)
+    ops.lauum(K, dinv)
     assert (torch.tril(K) - torch.tril(torch.linalg.inv(K0))).abs().max().item() < 1e-10
+
+
+@pytest.mark.parametrize("mode,prec", [(ops.GEMM_INT8_DIGITS, 7), (ops.GEMM_INT8_RNS, 16)])
+@pytest.mark.parametrize("n", [1664, 2560])          # 3 x 512 + 128 (ragged last block) and 5 x 512
+def test_inverse_with_dense_512_leaves_on_the_tensor_path(mode, prec, n):
+    """trtri / lauum as triangular MULTIPLIES whose leaves are K = 512 products against zero-padded dense copies of
+    the diagonal blocks (INT8 path, in place), with every product routed to the tensor path (no work floor)."""
+    b = 2
+    K0 = spd(b, n, seed=n + prec)
+    K = K0.clone()
+    dinv = ops.alloc_dinv(n, b, DEV)
+    info = torch.zeros(b, dtype=torch.int32, device=DEV)
+    ws = torch.empty(1 << 30, dtype=torch.uint8, device=DEV)
+    cfg = ops.gemm_cfg(ws, mode, prec, min_dim=128, alt_precision=0, min_mnk=0)
+    ops.potrf(K, dinv, info, cfg)
+    assert info.tolist() == [0] * b
+    Lref = torch.linalg.cholesky(K0)
+    assert rel_err(torch.tril(K), Lref) < 1e-12
+    ops.trtri(K, dinv, cfg)
+    assert rel_err(torch.tril(K), torch.linalg.inv(Lref)) < 1e-10
+    ops.lauum(K, dinv, cfg)
+    assert rel_err(torch.tril(K), torch.tril(torch.linalg.inv(K0))) < 1e-9
+    # potri = trtri + lauum in one call gives the same bits
+    K2 = K0.clone()
+    ops.potrf(K2, dinv, info, cfg)
+    ops.potri(K2, dinv, cfg)
+    assert torch.equal(torch.tril(K2), torch.tril(K))
 
 
 def test_potrf_reports_first_bad_pivot_per_batch_member():

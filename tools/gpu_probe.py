@@ -108,7 +108,7 @@ for n in (128, 384, 1024):
     e3 = (logdet - 2 * torch.log(torch.diagonal(Lref, dim1=1, dim2=2)).sum(-1)).abs().max().item()
     ops.trtri(Kmat, dinv)
     e4 = (torch.tril(Kmat) - torch.linalg.inv(Lref)).abs().max().item()
-    ops.lauum(Kmat)
+    ops.lauum(Kmat, dinv)
     e5 = (torch.tril(Kmat) - torch.tril(torch.linalg.inv(K0))).abs().max().item()
     out[f"chol_n{n}"] = dict(potrf=e1, alpha=e2, logdet=e3, trtri=e4, potri=e5, info=info.tolist())
     print(n, out[f"chol_n{n}"], flush=True)
