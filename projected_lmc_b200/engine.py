@@ -86,10 +86,11 @@ class LatentEngine:
     rns_moduli = int(__import__("os").environ.get("PLMC_RNS_MODULI", "16"))
     # precision of the explicit inverse of the training iteration (K^-1 = L^-T L^-1: trtri + lauum).  K^-1 feeds
     # ONLY the gradient sweep tr((alpha alpha^T - K^-1) dK): the loss, alpha and the log-determinant come from L,
-    # which keeps the full precision.  47-bit products there perturb the gradients at the 1e-13 level
-    # (tolerance 1e-6) and save a quarter (digits) / an eighth (rns) of those two steps; 0 = same as the main one.
+    # which keeps the full precision.  13 moduli = 43-bit operands (K <= 16384): measured against the CPU oracle the
+    # gradients do not move at all down to 12 moduli, even at cond(K) = 2e7 (tools/precision_table.py, DESIGN.md
+    # section 5); tolerance 1e-6.  Saves 3/16 of the INT8 products of those two steps; 0 = same as the main one.
     fp64_slices_kinv = int(__import__("os").environ.get("PLMC_FP64_SLICES_KINV", "6"))
-    rns_moduli_kinv = int(__import__("os").environ.get("PLMC_RNS_MODULI_KINV", "14"))
+    rns_moduli_kinv = int(__import__("os").environ.get("PLMC_RNS_MODULI_KINV", "13"))
     # fp32 grade (models whose tensors are float32; the reference's GPU default, experiments.py:4-8, tolerance 1e-4):
     # storage and accumulation stay FP64, but the operands of the large products carry 32 bits (10 moduli =
     # 10 INT8 products, or 4 digit planes = 10 products) in the factorisation AND the inverse: a third fewer

@@ -12,7 +12,7 @@ ROOT = Path(__file__).resolve().parents[1]
 
 
 def _eng(mode, **kw):
-    d = dict(fp64_slices=7, fp64_slices_kinv=6, fp64_min_dim=512, rns_moduli=16, rns_moduli_kinv=14)
+    d = dict(fp64_slices=7, fp64_slices_kinv=6, fp64_min_dim=512, rns_moduli=16, rns_moduli_kinv=14, rns_moduli_f32=10, fp64_slices_f32=4)
     d.update(kw)
     e = types.SimpleNamespace(**d)
     e.emulation_mode = lambda: mode
