@@ -4,8 +4,11 @@ plateau-based early stop -- without the per-iteration host synchronisation.
 
 The reference calls ``loss.item()`` every iteration to evaluate its stopping rule
 (experiments.py:275); here losses stay on the device and the same rule is evaluated over a
-buffered history every ``check_every`` iterations, so the GPU queue never drains in between
-(matters for launch-bound problems such as BASELINE config 1).
+buffered history every ``check_every`` iterations.  Inside an iteration the only host wait is on
+the event recorded right after the Cholesky factorisation (its per-latent status decides on the
+psd_safe_cholesky jitter retry); it is taken AFTER the solves, the inverse and the gradient
+sweep of the same iteration have been queued behind it, so the GPU queue does not drain on it
+(engine.LatentEngine.log_prob_and_grads).
 """
 from __future__ import annotations
 
