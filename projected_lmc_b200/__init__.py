@@ -5,6 +5,7 @@ The public model API (``ProjectedGPModel``, ``ProjectedLMCmll`` ...) mirrors
 hand-written CUDA kernels behind the C ABI in ``include/plmc_b200.h``.
 """
 from . import gp  # noqa: F401
+from ._cabi import PlmcError  # noqa: F401
 from .engine import LatentEngine, NanError, NotPSDError  # noqa: F401
 from .mixing import (LMCMixingMatrix, LowerTriangularParam, PositiveDiagonalParam, ScalarParam,  # noqa: F401
                      UpperTriangularParam)
@@ -16,5 +17,5 @@ __version__ = "0.1.0"
 __all__ = [
     "gp", "ProjectedGPModel", "ProjectedLMCmll", "ExactGPModel", "LMCMixingMatrix", "ScalarParam",
     "PositiveDiagonalParam", "UpperTriangularParam", "LowerTriangularParam", "handle_covar_",
-    "init_lmc_coefficients", "LatentEngine", "NotPSDError", "NanError", "projection_terms", "fit",
+    "init_lmc_coefficients", "LatentEngine", "NotPSDError", "NanError", "PlmcError", "projection_terms", "fit",
 ]

@@ -21,7 +21,7 @@ import warnings
 import torch
 
 from . import ops
-from ._cabi import npad as _npad
+from ._cabi import PlmcError, npad as _npad
 from .gp import settings
 
 
@@ -83,6 +83,7 @@ class LatentEngine:
     # of the triangular solves take the tensor path from m = 8192 on, the small products stay on DMMA)
     fp64_min_mnk = int(float(__import__("os").environ.get("PLMC_FP64_MIN_MNK", str(512 ** 3))))
     fp64_min_order = 1024    # matrices below this order are factorised in pure FP64
+    max_sweep_dims = 44      # csrc/gram.cu grad_sweep_kernel: (2*128*(dpad+1) + ...)*8 bytes <= 227 KB
     rns_moduli = int(__import__("os").environ.get("PLMC_RNS_MODULI", "16"))
     # precision of the explicit inverse of the training iteration (K^-1 = L^-T L^-1: trtri + lauum).  K^-1 feeds
     # ONLY the gradient sweep tr((alpha alpha^T - K^-1) dK): the loss, alpha and the log-determinant come from L,
@@ -195,6 +196,10 @@ class LatentEngine:
         """Per component: (Z [q, rows_pad, dpad_g], zn, X_g, xmean_g)."""
         out = []
         for kid, dims, ell, os_ in comps:
+            if len(dims) > self.max_sweep_dims:
+                # the gradient sweep stages full-width scaled inputs of both tile sides in shared memory
+                raise PlmcError(f"a kernel over {len(dims)} input dimensions exceeds the {self.max_sweep_dims} the "
+                                "gradient sweep stages in shared memory; split it with `decomp` into additive groups")
             Xg, xm = self._sub_inputs(X, dims)
             Z, zn = ops.scale_inputs(Xg, xm, ell, rows_pad)
             out.append((Z, zn, Xg, xm))

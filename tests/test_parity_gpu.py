@@ -312,6 +312,20 @@ def test_float32_model_runs_the_fp32_grade_on_the_tensor_path_within_1e_minus_4(
     assert m32.double()._engine.grade == "fp64"
 
 
+def test_more_than_44_dimensions_in_one_kernel_is_refused_with_the_remedy():
+    from projected_lmc_b200 import PlmcError
+
+    X, Y, _, _ = synth(200, 50, 4, 2, seed=3)
+    m = make_model(X, Y, 2, variant="PLMC_fast", kernel="rbf").cuda()
+    with pytest.raises(PlmcError, match="decomp"):
+        ProjectedLMCmll(m.likelihood, m)(m(X.cuda()), Y.cuda())
+    # ... and the remedy works: two additive groups of 25 dimensions
+    m2 = make_model(X, Y, 2, variant="PLMC_fast", kernel="rbf", decomp=[list(range(25)), list(range(25, 50))]).cuda()
+    loss = -ProjectedLMCmll(m2.likelihood, m2)(m2(X.cuda()), Y.cuda())
+    loss.backward()
+    assert torch.isfinite(loss)
+
+
 def test_not_psd_error_after_max_tries():
     from projected_lmc_b200 import NotPSDError
 
