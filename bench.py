@@ -255,6 +255,19 @@ def roofline_entry(eng, achieved, dmma_peak, peaks, peak_src, gemm_flops, gemm_l
             "frac_of_derived_peak": (achieved / derived) if achieved else None,
             "int8_products_per_fp64_product": pairs_eff,
         })
+        if mode == "rns":
+            # one ncu --set full capture of rns_gemm_kernel<2> (8192^3 FP64 product, 16 moduli; profiles/
+            # r02_ncu_summary.md): dram read 16.72 GB + write 1.07 GB per launch against 2.15 GB of operand planes +
+            # 1.07 GB of residues (algorithmic): each wave of 74 tile pairs re-streams its 8 + 9 operand panels from
+            # HBM; 35 % of DRAM peak, tensor pipe 85.5 % active: not traffic bound
+            common["traffic"] = 17.79e9
+            common["traffic_reference"] = ("ncu --set full, one 8192^3 rns_gemm_kernel<2> launch: 16.72 GB read + 1.07 GB "
+                                           "written, 3.2 GB algorithmic, tensor pipe 85.5 % active, DRAM 35 % "
+                                           "(profiles/r02_ncu_summary.md)")
+        else:
+            common["traffic"] = 8.50e9
+            common["traffic_reference"] = ("ncu --set full, one 8192^3 ozaki_gemm_kernel launch: 7.91 GB read + 0.60 GB "
+                                           "written, 1.47 GB algorithmic (profiles/r01_ozaki_gemm_v2_ncu_summary.md)")
     else:
         common.update({
             "kernel": "gemm_dmma_kernel (FP64 DMMA.8x8x4; potrf/trsm/trtri/lauum)",
@@ -366,7 +379,8 @@ def workload_config(args, cfg, world):
     p_tot, q_tot = model_shape(cfg, world, scaling)
     q_loc = -(-q_tot // world)
     out = {
-        "workload": f"{cfg['label']}: n={n}, d={cfg['d']}, {cfg['kernel']} ARD, fp64, PLMC variant (BDN=False), "
+        "workload": f"{cfg['label']}: n={n}, d={cfg['d']}, {cfg['kernel']} ARD, "
+                    f"{'float32 model (fp32-grade arithmetic)' if getattr(args, 'dtype', 'f64') == 'f32' else 'fp64'}, PLMC variant (BDN=False), "
                     f"{q_tot} latents and {p_tot} tasks on {world} GPU(s) ({q_loc} latents per GPU)",
         "n": n, "d": cfg["d"], "tasks_total": p_tot, "latents_total": q_tot,
         "latents_per_gpu": q_loc, "parallelism": f"latent-parallel x{world}",
@@ -418,7 +432,7 @@ def secondary_kernels(model, cfg, n, q_loc, phases, steps, peaks, peak_src):
           phases.get("gram", 0.0) / steps * 1e-3)
     entry("grad_sweep_kernel (fused backward sweep over the lower tiles of K^-1)", gram_bytes,
           phases.get("grad_sweep", 0.0) / steps * 1e-3)
-    Y = model.train_y
+    Y = model.train_y.to(torch.float64)          # float32 models: the projection kernels read an FP64 copy
     p = Y.shape[1]
     q = model.n_latents
     dev = Y.device

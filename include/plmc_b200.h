@@ -81,6 +81,9 @@ int plmc_init(void);
  * library, GEMM launches among them, and their algorithmic FLOPs (2*M*N*K over the
  * tiles actually computed).  Outputs are HOST pointers (may be NULL).            */
 int plmc_stats_reset(void);
+/* account for kernels launched outside the library's own launch sites: a caller that replays a CUDA graph captured
+ * over library calls adds the number of kernel nodes per replay */
+int plmc_stats_add(long long launches);
 int plmc_stats_get(long long* launches_host, long long* gemm_launches_host, double* gemm_flops_host);
 /* diagnostics: with tracing on, every GEMM of the factorisation layer is bracketed by CUDA events;
  * plmc_trace_report synchronises the device and prints time and FLOP rate per GEMM shape to stderr. */

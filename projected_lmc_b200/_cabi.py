@@ -36,6 +36,7 @@ _SIGNATURES = {
     "plmc_version": [],
     "plmc_init": [],
     "plmc_stats_reset": [],
+    "plmc_stats_add": [LL],
     "plmc_trace_enable": [I],
     "plmc_ozaki_debug": [P],
     "plmc_trace_report": [],

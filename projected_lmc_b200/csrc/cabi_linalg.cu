@@ -80,6 +80,11 @@ int plmc_stats_reset(void) {
     return PLMC_OK;
 }
 
+int plmc_stats_add(long long launches) {
+    note_launch(launches);
+    return PLMC_OK;
+}
+
 int plmc_stats_get(long long* launches_host, long long* gemm_launches_host, double* gemm_flops_host) {
     stats_get(launches_host, gemm_launches_host, gemm_flops_host);
     return PLMC_OK;

@@ -48,6 +48,7 @@ class LatentEngine:
         self._cfg_key = None
         self._pinned = None
         self._xsub = {}
+        self._graphs = {}
         self.last_jitter = None
         self.generation = 0     # bumped whenever ws['K'] is rewritten (prediction caches compare it)
 
@@ -65,6 +66,7 @@ class LatentEngine:
             )
             self._ws_key = key
             self._oz, self._cfg_key = None, None
+            self._graphs = {}
         self._configure_fp64(device, np_, q)
         return self._ws
 
@@ -83,6 +85,10 @@ class LatentEngine:
     # of the triangular solves take the tensor path from m = 8192 on, the small products stay on DMMA)
     fp64_min_mnk = int(float(__import__("os").environ.get("PLMC_FP64_MIN_MNK", str(512 ** 3))))
     fp64_min_order = 1024    # matrices below this order are factorised in pure FP64
+    # CUDA-graph replay of the engine part of a training step (launch-bound problems such as BASELINE config 1:
+    # ~130 library launches per iteration at n = 1000 become two graph launches).  Matrices of order <= this are
+    # captured after one eager warm-up call; 0 switches it off.
+    graph_max_order = int(__import__("os").environ.get("PLMC_GRAPH_MAX_ORDER", "4096"))
     max_sweep_dims = 44      # csrc/gram.cu grad_sweep_kernel: (2*128*(dpad+1) + ...)*8 bytes <= 227 KB
     rns_moduli = int(__import__("os").environ.get("PLMC_RNS_MODULI", "16"))
     # precision of the explicit inverse of the training iteration (K^-1 = L^-T L^-1: trtri + lauum).  K^-1 feeds
@@ -168,6 +174,7 @@ class LatentEngine:
 
     def release(self):
         """Drop the HBM workspaces and the plane scratch."""
+        self._graphs = {}
         self._ws, self._ws_key = None, None
         self._oz, self._cfg, self._cfg_key = None, (None, None), None
 
@@ -299,6 +306,8 @@ class LatentEngine:
         q = noise.shape[0]
         ws = self.workspace(X.device, q, n)
         np_ = ws["K"].shape[1]
+        if need_grad and self.profile is None and 0 < np_ <= self.graph_max_order and X.is_cuda:
+            return self._log_prob_and_grads_graphed(ws, X, TY, comps, noise, max_tries)
         mark = self._mark
         mark("start")
         scaled = self._scaled(X, comps, np_)
@@ -334,6 +343,105 @@ class LatentEngine:
             mark("retry")
             out = rest()                  # a jitter retry re-factorised K: redo what depended on it
         return out
+
+    # -- the same step as two replayed CUDA graphs (small problems) ---------------------------------------------
+    def _log_prob_and_grads_graphed(self, ws, X, TY, comps, noise, max_tries):
+        """Graph 1: scale -> Gram -> potrf -> status copy.  Graph 2: solves -> inverse -> sweep(s).  Inputs are copied
+        into static buffers, outputs cloned out of them; the status event sits between the two replays, so the
+        host waits for the factorisation only after the rest has been queued -- as in the eager path.  The first
+        call with a given (inputs, kernel structure, arithmetic) runs eagerly (lazy library initialisation must not
+        happen under capture), the second captures, later ones replay.  A failed factorisation falls back to the
+        eager retry loop."""
+        n = X.shape[0]
+        q = noise.shape[0]
+        np_ = ws["K"].shape[1]
+        key = (X.data_ptr(), X._version, tuple(X.shape), q, tuple((kid, tuple(dims), os_ is not None)
+                                                                  for kid, dims, ell, os_ in comps), self._cfg_key)
+        st = self._graphs.get(key)
+        if st is None:                      # warm-up: eager, with graphs disabled for this one call
+            self._graphs[key] = "warm"
+            old = self.graph_max_order
+            self.graph_max_order = 0
+            try:
+                return self.log_prob_and_grads(X, TY, comps, noise, True, max_tries)
+            finally:
+                self.graph_max_order = old
+        if st == "warm":
+            st = self._capture(ws, X, TY, comps, noise, n, np_, q)
+            self._graphs[key] = st
+        # refresh the static inputs, replay
+        st["TY"].copy_(TY)
+        st["noise"].copy_(noise)
+        for (kid, dims, ell, os_), (ell_s, os_s) in zip(comps, st["params"]):
+            ell_s.copy_(ell)
+            if os_ is not None:
+                os_s.copy_(os_)
+        self.generation += 1
+        st["g1"].replay()
+        if self._pinned is None or self._pinned.numel() != q + 1:
+            self._pinned = torch.empty((q + 1,), dtype=torch.int32).pin_memory()
+        self._pinned.copy_(ws["info"], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.generation += 1
+        st["g2"].replay()
+        ops.stats_add(st["launches"])            # the library kernels inside the two graphs
+        lp, alpha, g_noise, g_tensors = st["out"]
+        out = (lp.clone(), (-alpha, g_noise.clone(), [g.clone() for g in g_tensors]))
+        scaled = st["scaled"]
+        if self._gram_potrf_resolve(ev, ws, st["comps"], scaled, st["noise"], n, max_tries):
+            # jitter retry re-factorised K eagerly: finish the step eagerly as well
+            K, dinv = ws["K"], ws["dinv"]
+            z, alpha, quad, logdet = ops.solve_logdet(K, dinv, TY, n, ws["rhs"])
+            lp = -0.5 * (quad + logdet + n * math.log(2 * math.pi))
+            self.generation += 1
+            ops.trtri(K, dinv, self.cfg_kinv)
+            ops.lauum(K, dinv, self.cfg_kinv)
+            g_noise, g_tensors = None, []
+            for (kid, dims, ell, os_), (Z, zn, _, _) in zip(st["comps"], scaled):
+                g_ell, g_os, g_n = ops.grad_sweep(K, alpha, Z, zn, ell, kid, os_, n)
+                g_noise = g_n if g_noise is None else g_noise
+                g_tensors.append(g_ell)
+                if os_ is not None:
+                    g_tensors.append(g_os)
+            out = (lp, (-alpha, g_noise, g_tensors))
+        return out
+
+    def _capture(self, ws, X, TY, comps, noise, n, np_, q):
+        dev = X.device
+        K, dinv, info = ws["K"], ws["dinv"], ws["info"]
+        TY_s, noise_s = TY.clone(), noise.clone()
+        params = [(ell.clone(), None if os_ is None else os_.clone()) for kid, dims, ell, os_ in comps]
+        comps_s = [(kid, dims, e, o) for (kid, dims, _, _), (e, o) in zip(comps, params)]
+        for kid, dims, _, _ in comps_s:
+            self._sub_inputs(X, dims)            # column subsets / means are cached outside the graphs
+        torch.cuda.synchronize(dev)
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        launches0 = ops.stats_get()[0]
+        with torch.cuda.graph(g1):
+            scaled = self._scaled(X, comps_s, np_)
+            finite = torch.isfinite(noise_s).all()
+            for (kid, dims, ell, os_), (Z, zn, _, _) in zip(comps_s, scaled):
+                finite = finite & torch.isfinite(zn).all()
+                if os_ is not None:
+                    finite = finite & torch.isfinite(os_).all()
+            self._gram_all(comps_s, scaled, noise_s, K, n)
+            ops.potrf(K, dinv, info[:q], self.cfg_main)
+            info[q:] = (~finite).to(torch.int32)
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            z, alpha, quad, logdet = ops.solve_logdet(K, dinv, TY_s, n, ws["rhs"])
+            lp = -0.5 * (quad + logdet + n * math.log(2 * math.pi))
+            ops.trtri(K, dinv, self.cfg_kinv)
+            ops.lauum(K, dinv, self.cfg_kinv)
+            g_noise, g_tensors = None, []
+            for (kid, dims, ell, os_), (Z, zn, _, _) in zip(comps_s, scaled):
+                g_ell, g_os, g_n = ops.grad_sweep(K, alpha, Z, zn, ell, kid, os_, n)
+                g_noise = g_n if g_noise is None else g_noise
+                g_tensors.append(g_ell)
+                if os_ is not None:
+                    g_tensors.append(g_os)
+        return dict(g1=g1, g2=g2, TY=TY_s, noise=noise_s, params=params, comps=comps_s, scaled=scaled,
+                    out=(lp, alpha, g_noise, g_tensors), launches=ops.stats_get()[0] - launches0)
 
     # -- optional phase timing (CUDA events on the launch stream; used by bench.py) --
     profile = None

@@ -301,6 +301,10 @@ def stats_reset():
     check(_cabi.load().plmc_stats_reset(), "stats_reset")
 
 
+def stats_add(launches: int):
+    check(_cabi.load().plmc_stats_add(int(launches)), "stats_add")
+
+
 def trace_enable(on: bool):
     """Per-shape CUDA-event timing of every GEMM of the factorisation layer (diagnostics)."""
     check(_cabi.load().plmc_trace_enable(int(bool(on))), "trace_enable")

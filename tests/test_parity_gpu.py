@@ -326,6 +326,63 @@ def test_more_than_44_dimensions_in_one_kernel_is_refused_with_the_remedy():
     assert torch.isfinite(loss)
 
 
+@pytest.mark.parametrize("n,variant", [(700, "PLMC"), (1500, "PLMC_fast")])
+def test_cuda_graph_replay_of_the_engine_step_is_bit_identical_to_eager(n, variant):
+    """Small problems replay the engine part of the step as two CUDA graphs (LatentEngine.graph_max_order): same
+    bits as the eager launches over several optimiser steps (inputs are re-read on every replay), and the jitter
+    retry still works from inside the graphed path."""
+    from projected_lmc_b200.engine import LatentEngine
+
+    X, Y, _, _ = synth(n, 3, 5, 2, seed=n)
+    Xg, Yg = X.cuda(), Y.cuda()
+    hist = {}
+    old = LatentEngine.graph_max_order
+    try:
+        for order in (0, 4096):
+            LatentEngine.graph_max_order = order
+            m = make_model(X, Y, 2, variant=variant, kernel="matern52").cuda()
+            mll = ProjectedLMCmll(m.likelihood, m)
+            opt = torch.optim.SGD(m.parameters(), lr=1e-3)
+            out = []
+            for it in range(5):
+                opt.zero_grad(set_to_none=True)
+                loss = -mll(m(Xg), Yg)
+                loss.backward()
+                out.append((loss.item(), [p.grad.clone() for p in m.parameters()]))
+                opt.step()
+            hist[order] = out
+            if order:
+                assert any(isinstance(v, dict) for v in m._engine._graphs.values())      # really captured
+    finally:
+        LatentEngine.graph_max_order = old
+    for (l0, g0), (l1, g1) in zip(hist[0], hist[4096]):
+        assert l0 == l1 and all(torch.equal(a, b) for a, b in zip(g0, g1))
+
+
+def test_jitter_retry_from_the_graphed_path():
+    X, Y, _, _ = synth(300, 2, 4, 2, seed=77)
+    X[150:] = X[:150]
+    m = make_model(X, Y, 2, variant="PLMC", kernel="rbf", perturb=False, noise_thresh=-40.0)
+    with torch.no_grad():
+        m._base_kernel().raw_lengthscale.fill_(3.0)
+        m.likelihood.noise_covar.raw_noise.fill_(-60.0)
+    mc = cpu_copy(m)
+    m = m.cuda()
+    losses = []
+    with gp.settings.cholesky_max_tries(8), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for it in range(3):                      # eager warm-up, capture, replay: all three must retry and agree
+            for p in m.parameters():
+                p.grad = None
+            loss = -ProjectedLMCmll(m.likelihood, m)(m(X.cuda()), Y.cuda())
+            loss.backward()
+            losses.append(loss.item())
+            assert m._engine.last_jitter is not None and float(m._engine.last_jitter.max()) > 0
+        ref = -O.mll(oracle_params(mc), X, Y, max_tries=8)
+    assert losses[0] == losses[1] == losses[2]
+    assert abs(losses[0] - ref.item()) <= 1e-5 * abs(ref.item())
+
+
 def test_not_psd_error_after_max_tries():
     from projected_lmc_b200 import NotPSDError
 
