@@ -153,6 +153,15 @@ int plmc_potrf_batched(double* K, long long ld, long long stride, long long npad
 int plmc_trsm_batched(int op, const double* L, long long ld, long long stride, long long npad, int batch,
                       const double* dinv, double* B, long long ldb, long long strideb, long long m, double alpha,
                       const plmc_gemm_cfg* cfg, void* stream);
+/* op 2: B := alpha X B in place, X LOWER triangular [npad, npad] (its strict upper part is not read), B [npad, m],
+ * m % 128 == 0: the triangular MULTIPLY the explicit inverse is built from (dense 512-leaves on the tensor path,
+ * csrc/linalg.cu).  With X = inv(L) from plmc_trtri_batched it replaces the triangular solve of the predictive
+ * variance (gpytorch exact_predictive_covar, reached from projected_lmc.py:1134) at GEMM speed.  dinv: the side
+ * buffer of the factorisation calls; its dense-block scratch part is overwritten with copies of X's diagonal
+ * blocks.  Other ops: PLMC_ERR_BADARG.                                                                        */
+int plmc_trmm_batched(int op, const double* X, long long ld, long long stride, long long npad, int batch, double* dinv,
+                      double* B, long long ldb, long long strideb, long long m, double alpha,
+                      const plmc_gemm_cfg* cfg, void* stream);
 /* rhs [batch, npad, 128] workspace (the first npad entries per member are used).
  * Fills z = L^-1 y, alpha = L^-T z (both [batch, ldv]), quad[b] = |z|^2,
  * logdet[b] = 2 sum log L_ii.  Two HBM-bound block substitutions: every tile of

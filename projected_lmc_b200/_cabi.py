@@ -55,6 +55,7 @@ _SIGNATURES = {
     "plmc_cross_gram_bwd": [P, LL, P, LL, P, LL, LL, I, P, P, P, P, P, P, LL, LL, I, I, I, P],
     "plmc_potrf_batched": [P, LL, LL, LL, I, P, P, CFG, P],
     "plmc_trsm_batched": [I, P, LL, LL, LL, I, P, P, LL, LL, LL, D, CFG, P],
+    "plmc_trmm_batched": [I, P, LL, LL, LL, I, P, P, LL, LL, LL, D, CFG, P],
     "plmc_solve_logdet": [P, LL, LL, LL, LL, I, P, P, LL, P, P, P, LL, P, P, P],
     "plmc_trtri_batched": [P, LL, LL, LL, I, P, CFG, P],
     "plmc_lauum_batched": [P, LL, LL, LL, I, P, CFG, P],

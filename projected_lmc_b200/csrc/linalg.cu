@@ -332,6 +332,13 @@ static void trtri_rec(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
     trmm_lln(cx, L22, n2, D, blk0 + n1 / LEAF, L21, n1, -1.0);
 }
 
+// B := alpha X B for a lower-triangular X; the dense copies of X's diagonal 512-blocks are (re)written first
+void trmm_lln_lower(LaCtx& cx, BMat X, int n, DinvBuf D, BMat B, int m, double alpha, bool fill_dense) {
+    if (cx.status || n <= 0 || m <= 0) return;
+    if (fill_dense) dense_diag_copy(cx, X, n, D, 0);
+    trmm_lln(cx, X, n, D, 0, B, m, alpha);
+}
+
 void trtri_lower(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
     if (cx.status || n <= 0) return;
     trtri_rec(cx, L, n, D, blk0);

@@ -96,6 +96,9 @@ void trsm_llt(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m
 void trtri_lower(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0);
 // L -> lower(L^T L) in place; D supplies (and, with fill_dense, receives) the dense copies of L's diagonal blocks
 void lauum_lower(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, bool fill_dense);
+// B := alpha * X * B  (X lower n x n, B n x m): triangular multiply with dense 512-leaves; fill_dense refreshes
+// the dense copies of X's diagonal blocks in D first (not needed right after trtri_lower on the same matrix)
+void trmm_lln_lower(LaCtx& cx, BMat X, int n, DinvBuf D, BMat B, int m, double alpha, bool fill_dense);
 // B := T^T * B  (T lower n x n, B n x m)
 void trmm_llt(LaCtx& cx, BMat T, int n, DinvBuf D, long long blk0, BMat B, int m);
 

@@ -517,9 +517,34 @@ class LatentEngine:
             st["L"].data_ptr() == self._ws["K"].data_ptr()
 
     @staticmethod
-    def tile_points(q: int, np_: int, budget_bytes: int = 6 << 30) -> int:
+    def tile_points(q: int, np_: int, budget_bytes: int = None, device=None) -> int:
+        """Test points per cross-Gram tile [q, npad, mt]: as wide as the GEMMs like (8192) when a quarter of the
+        free HBM holds the tile, never below what 6 GB hold."""
+        if budget_bytes is None:
+            budget_bytes = 6 << 30
+            if device is not None and torch.cuda.is_available():
+                budget_bytes = max(budget_bytes, torch.cuda.mem_get_info(device)[0] // 4)
         mt = (budget_bytes // (q * np_ * 8) // 128) * 128
         return int(max(128, min(8192, mt)))
+
+    # Predictive variances need V = L^-1 K*.  A triangular SOLVE recurses down to 128-leaves (K = 128 products,
+    # FP64-pipe bound); with the explicit inverse X = L^-1 (plmc_trtri_batched, n^3/3 per latent, once per
+    # parameter state) V = X K* is a triangular MULTIPLY with dense 512-leaves: the same q n^2 n* FLOP at GEMM
+    # speed.  "auto": invert once the points predicted with this state reach n/2 (the break-even of the extra
+    # n^3/3); True / False force either path.
+    predict_inverse = {"0": False, "1": True}.get(__import__("os").environ.get("PLMC_PREDICT_INVERSE", "auto"), "auto")
+
+    def _maybe_invert(self, st, ns):
+        if st.get("inverted"):
+            return True
+        st["points"] = st.get("points", 0) + ns
+        want = self.predict_inverse
+        if want == "auto":
+            want = st["points"] * 2 >= st["n"]
+        if want:
+            ops.trtri(st["L"], st["dinv"], self.cfg_main)      # L -> L^-1 in place (alpha is already computed)
+            st["inverted"] = True
+        return bool(want)
 
     def predict_latents(self, st, Xs, need_var=True, tile=None):
         """Latent posterior means / variances at Xs: ([q, n*], [q, n*])."""
@@ -530,7 +555,8 @@ class LatentEngine:
         if not self.state_is_current(st):
             raise RuntimeError("stale prediction state: the engine workspace was rewritten after factorize()")
         self._configure_fp64(dev, np_, q)
-        mt_full = tile or self.tile_points(q, np_)
+        mt_full = tile or self.tile_points(q, np_, device=dev)
+        inverted = self._maybe_invert(st, ns) if need_var else False
         lat_mean = torch.empty((q, ns), dtype=torch.float64, device=dev)
         lat_var = torch.empty((q, ns), dtype=torch.float64, device=dev) if need_var else None
         Kx = None
@@ -548,6 +574,9 @@ class LatentEngine:
                 ops.cross_gram(Z, zn, Zt, znt, kid, os_, Kx, n, mt, accumulate=(g > 0))
             lat_mean[:, s0:s0 + cnt] = ops.latent_mean(Kx, st["alpha"], n, mt)[:, :cnt]
             if need_var:
-                ops.trsm(2, st["L"], st["dinv"], Kx, 1.0, self.cfg_main)
+                if inverted:
+                    ops.trmm(2, st["L"], st["dinv"], Kx, 1.0, self.cfg_main)
+                else:
+                    ops.trsm(2, st["L"], st["dinv"], Kx, 1.0, self.cfg_main)
                 lat_var[:, s0:s0 + cnt] = ops.latent_var(Kx, st["prior_var"], mt)[:, :cnt]
         return lat_mean, lat_var

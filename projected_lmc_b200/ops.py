@@ -105,6 +105,20 @@ def trsm(op: int, L, dinv, B, alpha=1.0, cfg=None):
 
 
 @_on_device
+def trmm(op: int, X, dinv, B, alpha=1.0, cfg=None):
+    """op 2: B := alpha X B in place for lower-triangular X [batch, npad, npad] (e.g. inv(L) from trtri) and
+    B [batch, npad, m]; the dense-block scratch part of dinv is overwritten."""
+    b, np_, _ = X.shape
+    check(
+        lib().plmc_trmm_batched(
+            op, ptr(X), X.stride(1), X.stride(0), np_, b, ptr(dinv), ptr(B), B.stride(1), B.stride(0), B.shape[2],
+            float(alpha), _cfgp(cfg), stream(),
+        ),
+        "trmm",
+    )
+
+
+@_on_device
 def solve_logdet(L, dinv, y, n, rhs=None):
     """z = L^-1 y, alpha = L^-T z, |z|^2, 2 sum log L_ii for y [batch, >=n]."""
     b, np_, _ = L.shape

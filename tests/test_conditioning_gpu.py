@@ -65,11 +65,17 @@ def test_long_lengthscales_with_noise_at_the_floor_match_the_oracle(gemm_mode, n
         if refg[name].grad is not None:
             assert rel_err(prm.grad, refg[name].grad) <= 1e-6, (name, cond)
     m.eval()
+    m._engine.predict_inverse = False                  # variance term by triangular solves with L
     with torch.no_grad(), warnings.catch_warnings():
         warnings.simplefilter("ignore")
         pred = m.full_likelihood()(m(Xs.cuda()))
         mean_ref, _, var_ref = O.predict(oracle_params(mc), X, Y, Xs)
+        m._engine.predict_inverse = True               # ... and by a triangular multiply with the explicit L^-1
+        m._pred_cache = None
+        pred_inv = m.full_likelihood()(m(Xs.cuda()))
+        assert m._pred_cache["inverted"]
     assert rel_err(pred.mean, mean_ref) <= 1e-6 and rel_err(pred.variance, var_ref) <= 1e-6
+    assert rel_err(pred_inv.mean, mean_ref) <= 1e-6 and rel_err(pred_inv.variance, var_ref) <= 1e-6
 
 
 def _cfg(mode, device, n):
@@ -239,3 +245,27 @@ def test_prediction_cache_is_invalidated_when_the_workspace_is_rewritten():
         p3 = m(Xsg)
     for p in (p1, p2, p3):
         assert torch.equal(p.mean, p0.mean) and torch.equal(p.variance, p0.variance)
+
+
+def test_prediction_switches_to_the_explicit_inverse_after_half_n_points():
+    """engine.predict_inverse = "auto": triangular solves until the points predicted with one factorisation reach
+    n/2, then the factor is inverted in place and the variance term becomes a triangular multiply -- same results
+    before and after the switch, and a parameter change starts over."""
+    X, Y, Xs, _ = synth(900, 3, 5, 2, seed=5, ns=200)
+    m = make_model(X, Y, 2, variant="PLMC", kernel="matern52")
+    mc = cpu_copy(m)
+    m = m.cuda().eval()
+    assert m._engine.predict_inverse == "auto"
+    Xsg = Xs.cuda()
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, var_ref, _ = O.predict(oracle_params(mc), X, Y, Xs)
+        v1 = m(Xsg).variance
+        assert not m._pred_cache.get("inverted")             # 200 < 450
+        v2 = m(Xsg).variance
+        assert not m._pred_cache.get("inverted")             # 400 < 450
+        v3 = m(Xsg).variance
+        assert m._pred_cache["inverted"]                     # 600 >= 450
+        v4 = m(Xsg).variance
+    assert torch.equal(v1, v2) and torch.equal(v3, v4)
+    assert rel_err(v1, var_ref) <= 1e-7 and rel_err(v3, var_ref) <= 1e-7

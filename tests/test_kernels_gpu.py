@@ -161,6 +161,35 @@ def test_trsm_ops(op):
     assert (B - ref).abs().max().item() < 1e-10
 
 
+@pytest.mark.parametrize("mode,prec", [(None, 0), (ops.GEMM_INT8_DIGITS, 7), (ops.GEMM_INT8_RNS, 16)])
+@pytest.mark.parametrize("n,m", [(640, 256), (1664, 1024)])      # ragged last 512-block in both
+def test_trmm_with_the_explicit_inverse_equals_the_triangular_solve(mode, prec, n, m):
+    """plmc_trmm_batched op 2 (B := a X B, X = inv(L) from trtri): the predictive-variance product as a triangular
+    multiply; same result as the solve with L, in pure FP64 (128-leaves) and on the tensor path (dense 512-leaves)."""
+    b = 2
+    K0 = spd(b, n, seed=n)
+    K = K0.clone()
+    dinv = ops.alloc_dinv(n, b, DEV)
+    info = torch.zeros(b, dtype=torch.int32, device=DEV)
+    cfg = None
+    if mode is not None:
+        ws = torch.empty(1 << 30, dtype=torch.uint8, device=DEV)
+        cfg = ops.gemm_cfg(ws, mode, prec, min_dim=128, alt_precision=0, min_mnk=0)
+    ops.potrf(K, dinv, info, cfg)
+    Lref = torch.linalg.cholesky(K0)
+    B0 = rnd(b, n, m, seed=9)
+    ref = torch.linalg.solve_triangular(Lref, -0.5 * B0, upper=False)
+    Bs = B0.clone()
+    ops.trsm(2, K, dinv, Bs, alpha=-0.5, cfg=cfg)
+    ops.trtri(K, dinv, cfg)
+    K.add_(torch.triu(torch.full_like(K, float("nan")), 1))              # the strict upper part is never read
+    Bm = B0.clone()
+    ops.trmm(2, K, dinv, Bm, alpha=-0.5, cfg=cfg)
+    assert rel_err(Bs, ref) < 1e-11 and rel_err(Bm, ref) < 1e-11
+    with pytest.raises(Exception):
+        ops.trmm(0, K, dinv, Bm)
+
+
 @pytest.mark.parametrize("n,p,q", [(1, 1, 1), (63, 7, 4), (1000, 50, 10), (4097, 65, 33), (513, 500, 32)])
 def test_projection_fwd_bwd(n, p, q):
     Y, T = rnd(n, p, seed=1), rnd(p, q, seed=2)
