@@ -182,8 +182,12 @@ int plmc_potri_batched(double* L, long long ld, long long stride, long long npad
 /* ---- (4) fused backward: autograd of log_prob through the kernel
  * (experiments.py:270 loss.backward()).  With W = 1/2 (alpha alpha^T - K^-1):
  *   g_noise[l] = tr W ; g_os[l] = sum W o k ; g_ell[l,k] = d lp / d ell[l,k].
- * Kinv: lower tiles of K^-1; partial: workspace of plmc_grad_ws(...) bytes.    */
+ * Kinv: lower tiles of K^-1; Z, zn: scaled inputs and their squared norms (plmc_scale_inputs); partial: workspace
+ * of plmc_grad_ws(...) bytes.  d <= 24: both contractions (distances, A Z) on the FP64 tensor cores.             */
 long long plmc_grad_ws(long long npad, int d, int q);
+/* diagnostics (process-wide, like plmc_trace_enable): direct != 0 forces the direct-difference sweep kernel that
+ * otherwise only serves inputs of more than 24 dimensions; 0 restores the default (GEMM form on DMMA for d <= 24) */
+int plmc_sweep_debug(int direct);
 int plmc_grad_sweep(const double* Kinv, long long ld, long long stride, const double* alpha, long long lda_vec,
                     const double* Z, const double* zn, const double* ell, int kernel_id, const double* os,
                     double* g_ell, double* g_os, double* g_noise, double* partial, long long n, long long npad, int d,

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "plmc_lauum_batched": [P, LL, LL, LL, I, P, CFG, P],
     "plmc_potri_batched": [P, LL, LL, LL, I, P, CFG, P],
     "plmc_grad_ws": [LL, I, I],
+    "plmc_sweep_debug": [I],
     "plmc_grad_sweep": [P, LL, LL, P, LL, P, P, P, I, P, P, P, P, P, LL, LL, I, I, I, P],
     "plmc_latent_mean": [P, LL, LL, P, LL, P, LL, LL, LL, I, P],
     "plmc_latent_var": [P, LL, LL, P, P, LL, LL, LL, I, P],

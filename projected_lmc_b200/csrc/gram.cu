@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1)
                 const long long gj = j0 + cl;
                 double w = (gj < gi) ? 2.0 : (gj == gi ? 1.0 : 0.0);
                 if (gi >= n || gj >= n) w = 0.0;
-                const double Wij = 0.5 * (a_i * aj[cl] - (e ? kv.y : kv.x));
+                const double Wij = (w != 0.0) ? 0.5 * (a_i * aj[cl] - (e ? kv.y : kv.x)) : 0.0;
                 double kk, dk;
                 kernel_value_grad<KID>(stage[(pr * 2 + e) * GR_THREADS + tid], kk, dk);
                 s_os = fma(w * Wij, kk, s_os);
@@ -343,6 +343,268 @@ __global__ void __launch_bounds__(GR_THREADS, 1)
     if (tid < nacc) partial[((long long)l * gridDim.x + blockIdx.x) * nacc + tid] = cta_acc[tid];
 }
 
+// ---------------------------------------------------------------------------
+// Fused backward sweep, GEMM form (input dimension d <= 24; the kernel above remains for wider inputs).
+// Both contractions of the sweep run on the FP64 tensor cores and the CTA is small enough for two per SM, so the
+// load / DMMA phases of one overlap the transcendental phase of the other:
+//   1. cross term  S = Zi Zj^T (DMMA)  ->  s_ij = max(|zi|^2 + |zj|^2 - 2 S_ij, 0), exactly the forward Gram's s;
+//   2. transform (rolled loop over the thread's entries, parked in the tile buffer At):
+//        A_ij = w_ij W_ij os dk/ds(s_ij)   (0 on the diagonal),   s_os += w W k,   s_tr += W_ii;
+//   3. sum_ij A_ij (z_ik - z_jk)^2 = sum_i z_ik (ra_i z_ik - 2 U_ik) + sum_j ca_j z_jk^2   with U = A Zj (DMMA,
+//      64 x 128 x d), ra / ca the row / column sums of A (ra falls out of the A fragments the DMMA loads anyway).
+// A 128 x 128 tile of the lower triangle is processed as two 64-row halves.  Shared memory (d <= 24): Zj 128 x 28,
+// Zi 64 x 28, At 64 x 132 doubles + 3 KB = 111 KB, registers <= 128: two CTAs per SM.
+// Per-thread partial sums live in registers across the CTA's whole tile sequence; one fixed-order reduction at
+// the end (deterministic).  partial layout as above: [q, gridDim.x, dpad + 2].
+// ---------------------------------------------------------------------------
+constexpr int SW_AS = 132;   // row stride of At: = 4 mod 16, conflict-free DMMA A-fragment loads
+__host__ __device__ inline int sweep_lds(int dpad) { return (dpad % 8 == 0) ? dpad + 4 : dpad + 8; }
+__host__ __device__ inline size_t sweep2_smem(int dpad) {
+    return (size_t)((128 + 64) * sweep_lds(dpad) + 64 * SW_AS + 128 + 256) * 8;
+}
+
+template <int KID, bool INTERIOR>
+__device__ __forceinline__ void sweep_transform(double* __restrict__ At, const double* __restrict__ aj,
+                                                const double* __restrict__ Kl, long long ld, long long ih0,
+                                                long long j0, long long n, int wm, int wn, int g, int t,
+                                                const double (&ai)[4], double osl, double& s_os, double& s_tr) {
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        const int cl = wn * 32 + j * 8 + 2 * t;
+        const long long gj = j0 + cl;
+        const double2 ajv = *reinterpret_cast<const double2*>(aj + cl);
+        double2 kv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            kv[i] = __ldg(reinterpret_cast<const double2*>(Kl + (ih0 + wm * 32 + i * 8 + g) * ld + gj));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rl = wm * 32 + i * 8 + g;
+            const long long gi = ih0 + rl;
+            double2* slot = reinterpret_cast<double2*>(At + rl * SW_AS + cl);
+            const double2 sv = *slot;
+            double out[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double raw = fma(ai[i], e ? ajv.y : ajv.x, -(e ? kv[i].y : kv[i].x));   // 2 W_ij
+                double kk, dk;
+                kernel_value_grad<KID>(e ? sv.y : sv.x, kk, dk);
+                if (INTERIOR) {                       // strictly below the diagonal, no padding: w/2 = 1
+                    s_os = fma(raw, kk, s_os);
+                    out[e] = raw * (osl * dk);
+                } else {
+                    const long long gje = gj + e;
+                    double w = (gje < gi) ? 1.0 : ((gje == gi) ? 0.5 : 0.0);
+                    if (gi >= n || gje >= n) w = 0.0;
+                    const double c1 = (w != 0.0) ? w * raw : 0.0;   // entries above the diagonal are never used
+                    s_os = fma(c1, kk, s_os);
+                    if (gje == gi) s_tr += c1;
+                    out[e] = (gje == gi) ? 0.0 : c1 * (osl * dk);
+                }
+            }
+            *slot = make_double2(out[0], out[1]);
+        }
+    }
+}
+
+template <int KID, int NB>
+__global__ void __launch_bounds__(GR_THREADS, 2)
+    grad_sweep2_kernel(const double* __restrict__ Kinv, long long ld, long long stride,
+                       const double* __restrict__ alpha, long long lda_vec, const double* __restrict__ Z,
+                       const double* __restrict__ zn, const double* __restrict__ os, double* __restrict__ partial,
+                       long long n, long long npad, int dpad, long long ntiles) {
+    extern __shared__ __align__(16) double sm[];
+    const int lds = sweep_lds(dpad);
+    double* Zj = sm;                     // [128][lds]
+    double* Zi = Zj + 128 * lds;         // [64][lds]
+    double* At = Zi + 64 * lds;          // [64][SW_AS]
+    double* aj = At + 64 * SW_AS;        // [128]
+    double* ca2 = aj + 128;              // [2][128]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int l = blockIdx.z;
+    const int nacc = dpad + 2;
+    const double osl = os ? os[l] : 1.0;
+    const double* Kl = Kinv + (long long)l * stride;
+    const double* al = alpha + (long long)l * lda_vec;
+    const double* Zl = Z + (long long)l * npad * dpad;
+    const double* znl = zn + (long long)l * npad;
+    const int dp2 = dpad >> 1;           // double2 per row of Z
+
+    // the padding columns [dpad, lds) of the staged inputs are read by the last 8-wide dimension block: zero, once
+    for (int idx = tid; idx < 192 * (lds - dpad); idx += GR_THREADS) {
+        const int r = idx / (lds - dpad), c = idx - r * (lds - dpad);
+        Zj[r * lds + dpad + c] = 0.0;    // Zi follows Zj with the same row stride: rows 128..191 are Zi
+    }
+
+    double gacc[NB][2];                  // dims nb*8 + 2t + e, summed over this thread's rows (all tiles)
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) gacc[nb][0] = gacc[nb][1] = 0.0;
+    double cacc = 0.0;                   // dim = lane, column-side term
+    double s_os = 0.0, s_tr = 0.0;
+
+    for (long long b = blockIdx.x; b < ntiles; b += gridDim.x) {
+        int r = (int)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+        while ((long long)(r + 1) * (r + 2) / 2 <= b) ++r;
+        while ((long long)r * (r + 1) / 2 > b) --r;
+        const int ti = r, tj = (int)(b - (long long)r * (r + 1) / 2);
+        const long long i0 = (long long)ti * 128, j0 = (long long)tj * 128;
+        const bool interior = (ti != tj) && (i0 + 128 <= n);
+
+        __syncthreads();                 // everyone is done with Zj / aj / ca2 of the previous tile
+        {
+            const int rr = tid >> 1;
+            const double2* src = reinterpret_cast<const double2*>(Zl + (j0 + rr) * dpad);
+            double2* dst = reinterpret_cast<double2*>(Zj + rr * lds);
+            for (int c = tid & 1; c < dp2; c += 2) dst[c] = __ldg(src + c);
+            if (tid < 128) aj[tid] = (j0 + tid < n) ? al[j0 + tid] : 0.0;
+        }
+        double nj[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double2 v = __ldg(reinterpret_cast<const double2*>(znl + j0 + wn * 32 + j * 8 + 2 * t));
+            nj[j][0] = v.x;
+            nj[j][1] = v.y;
+        }
+
+        for (int h = 0; h < 2; ++h) {
+            const long long ih0 = i0 + 64 * h;
+            {
+                const int rr = tid >> 2;
+                const double2* src = reinterpret_cast<const double2*>(Zl + (ih0 + rr) * dpad);
+                double2* dst = reinterpret_cast<double2*>(Zi + rr * lds);
+                for (int c = tid & 3; c < dp2; c += 4) dst[c] = __ldg(src + c);
+            }
+            double ai[4], ni[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long gi = ih0 + wm * 32 + i * 8 + g;
+                ai[i] = (gi < n) ? __ldg(al + gi) : 0.0;
+                ni[i] = __ldg(znl + gi);
+            }
+            __syncthreads();             // Zi (and, for h = 0, Zj / aj) staged
+
+            // ---- 1. cross term on DMMA, squared distances into At
+            {
+                double acc[4][4][2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+                const double* pa = Zi + (wm * 32 + g) * lds + t;
+                const double* pb = Zj + (wn * 32 + g) * lds + t;
+                for (int k0 = 0; k0 < dpad; k0 += 4) {
+                    double af[4], bf[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) af[i] = pa[i * 8 * lds + k0];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bf[j] = pb[j * 8 * lds + k0];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double s0 = dmax(fma(-2.0, acc[i][j][0], ni[i] + nj[j][0]), 0.0);
+                        const double s1 = dmax(fma(-2.0, acc[i][j][1], ni[i] + nj[j][1]), 0.0);
+                        *reinterpret_cast<double2*>(At + (wm * 32 + i * 8 + g) * SW_AS + wn * 32 + j * 8 + 2 * t) =
+                            make_double2(s0, s1);
+                    }
+            }
+            // ---- 2. transform in place (a thread reads back only the slots it wrote: no barrier)
+            if (interior)
+                sweep_transform<KID, true>(At, aj, Kl, ld, ih0, j0, n, wm, wn, g, t, ai, osl, s_os, s_tr);
+            else
+                sweep_transform<KID, false>(At, aj, Kl, ld, ih0, j0, n, wm, wn, g, t, ai, osl, s_os, s_tr);
+            __syncthreads();             // At = A complete
+
+            // ---- 3. U = A Zj on DMMA (warp w: rows 8w..8w+7), row sums from the same fragments, column sums
+            {
+                double u[NB][2];
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) u[nb][0] = u[nb][1] = 0.0;
+                double ra = 0.0;
+                const double* pa = At + (warp * 8 + g) * SW_AS + t;
+                const double* pb = Zj + t * lds + g;
+#pragma unroll 4
+                for (int kk = 0; kk < 32; ++kk) {
+                    const double a = pa[kk * 4];
+                    ra += a;
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) dmma884(u[nb][0], u[nb][1], a, pb[kk * 4 * lds + nb * 8]);
+                }
+                ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+                ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+                {
+                    const int col = tid & 127, hf = tid >> 7;
+                    const double* pc = At + (hf * 32) * SW_AS + col;
+                    double c = 0.0;
+#pragma unroll 8
+                    for (int rr = 0; rr < 32; ++rr) c += pc[rr * SW_AS];
+                    ca2[hf * 128 + col] = c;
+                }
+                const double* pz = Zi + (warp * 8 + g) * lds + 2 * t;
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                    const double2 z = *reinterpret_cast<const double2*>(pz + nb * 8);
+                    gacc[nb][0] = fma(z.x, fma(ra, z.x, -2.0 * u[nb][0]), gacc[nb][0]);
+                    gacc[nb][1] = fma(z.y, fma(ra, z.y, -2.0 * u[nb][1]), gacc[nb][1]);
+                }
+            }
+            __syncthreads();             // ca2 visible; At / Zi free for the next half
+            if (lane < NB * 8) {
+#pragma unroll 4
+                for (int m = 0; m < 16; ++m) {
+                    const int jj = warp + 8 * m;
+                    const double zz = Zj[jj * lds + lane];
+                    cacc = fma((ca2[jj] + ca2[128 + jj]) * zz, zz, cacc);
+                }
+            }
+        }
+    }
+
+    // ---- fixed-order reduction of the per-thread sums: over the row lanes g, then over the 8 warps
+    __syncthreads();
+    double* red = At;                    // [8][nacc] (+ [8][NB*8] for the column-side sums)
+    double* red2 = At + 8 * nacc;
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double v = gacc[nb][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            const int k = nb * 8 + 2 * t + e;
+            if (g == 0 && k < dpad) red[warp * nacc + k] = v;
+        }
+    if (lane < NB * 8) red2[warp * (NB * 8) + lane] = cacc;
+    s_os = warp_sum(s_os);
+    s_tr = warp_sum(s_tr);
+    if (lane == 0) {
+        red[warp * nacc + dpad] = s_os;
+        red[warp * nacc + dpad + 1] = s_tr;
+    }
+    __syncthreads();
+    if (tid < nacc) {
+        double s = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) s += red[w8 * nacc + tid];
+        if (tid < dpad) {
+            double c = 0.0;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) c += red2[w8 * (NB * 8) + tid];
+            s += c;
+        }
+        partial[((long long)l * gridDim.x + blockIdx.x) * nacc + tid] = s;
+    }
+}
+
 // g_ell[l,k] = -(2/ell[l,k]) * sum_c partial[l,c,k] ; g_os, g_noise likewise
 __global__ void grad_reduce_kernel(const double* __restrict__ partial, int chunks, int d, int dpad,
                                    const double* __restrict__ ell, double* __restrict__ g_ell,
@@ -366,6 +628,9 @@ static inline int sweep_ctas(long long ntiles) { return (int)(ntiles < 592 ? nti
 }  // namespace plmc
 
 using namespace plmc;
+
+// diagnostics (tests): force the direct-difference sweep kernel for every input dimension
+static bool g_sweep_direct = false;
 
 template <int MODE>
 static int launch_gram(int kernel_id, dim3 grid, size_t smem, cudaStream_t st, const double* Zr, const double* znr,
@@ -459,6 +724,11 @@ int plmc_cross_gram(const double* Ztrain, const double* zntrain, const double* Z
                           npad, Ztest, zntest, mt_rows_pad, os, nullptr, Kx, ldx, stride, n, dpad, (int)tc, accumulate);
 }
 
+int plmc_sweep_debug(int direct) {
+    g_sweep_direct = direct != 0;
+    return PLMC_OK;
+}
+
 long long plmc_grad_ws(long long npad, int d, int q) {
     if (npad <= 0 || d <= 0 || q <= 0) return 0;
     const long long tm = npad / 128;
@@ -470,8 +740,7 @@ int plmc_grad_sweep(const double* Kinv, long long ld, long long stride, const do
                     const double* Z, const double* zn, const double* ell, int kernel_id, const double* os,
                     double* g_ell, double* g_os, double* g_noise, double* partial, long long n, long long npad, int d,
                     int dpad, int q, void* stream) {
-    (void)zn;
-    if (!Kinv || !alpha || !Z || !ell || !g_ell || !g_noise || !partial || n <= 0 || npad < n || (npad % 128) ||
+    if (!Kinv || !alpha || !Z || !zn || !ell || !g_ell || !g_noise || !partial || n <= 0 || npad < n || (npad % 128) ||
         ld < npad || (ld & 1) || d <= 0 || dpad < d || (dpad & 3) || dpad != ((d + 3) / 4) * 4 || q <= 0 ||
         q > 65535 || lda_vec < n)
         return PLMC_ERR_BADARG;
@@ -479,6 +748,38 @@ int plmc_grad_sweep(const double* Kinv, long long ld, long long stride, const do
     const long long tm = npad / 128;
     const long long ntiles = tm * (tm + 1) / 2;
     const int ctas = sweep_ctas(ntiles);
+    if (dpad <= 24 && !g_sweep_direct) {
+        // GEMM form on the FP64 tensor cores, two CTAs per SM
+        const size_t smem2 = sweep2_smem(dpad);
+        dim3 grid2(ctas, 1, q);
+#define PLMC_SWEEP2_LAUNCH(KID, NB)                                                                                \
+    {                                                                                                              \
+        cudaFuncSetAttribute(grad_sweep2_kernel<KID, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2); \
+        grad_sweep2_kernel<KID, NB><<<grid2, GR_THREADS, smem2, st>>>(Kinv, ld, stride, alpha, lda_vec, Z, zn, os,   \
+                                                                     partial, n, npad, dpad, ntiles);              \
+    }
+#define PLMC_SWEEP2_CASE(KID)                                   \
+    case KID:                                                   \
+        if (dpad <= 8) PLMC_SWEEP2_LAUNCH(KID, 1)               \
+        else if (dpad <= 16) PLMC_SWEEP2_LAUNCH(KID, 2)         \
+        else PLMC_SWEEP2_LAUNCH(KID, 3)                         \
+        break;
+        switch (kernel_id) {
+            PLMC_SWEEP2_CASE(0)
+            PLMC_SWEEP2_CASE(1)
+            PLMC_SWEEP2_CASE(2)
+            PLMC_SWEEP2_CASE(3)
+            default: return PLMC_ERR_BADARG;
+        }
+#undef PLMC_SWEEP2_CASE
+#undef PLMC_SWEEP2_LAUNCH
+        PLMC_CHECK_LAUNCH();
+        note_launch(1);
+        grad_reduce_kernel<<<q, 64, 0, st>>>(partial, ctas, d, dpad, ell, g_ell, g_os, g_noise);
+        PLMC_CHECK_LAUNCH();
+        note_launch(1);
+        return PLMC_OK;
+    }
     const size_t smem = (size_t)(2 * 128 * (dpad + 1) + 256 + 9 * (dpad + 2) + 64 * GR_THREADS) * 8;
     if (smem > 227 * 1024) return PLMC_ERR_BADARG;
     dim3 grid(ctas, 1, q);

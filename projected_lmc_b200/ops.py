@@ -319,6 +319,11 @@ def stats_add(launches: int):
     check(_cabi.load().plmc_stats_add(int(launches)), "stats_add")
 
 
+def sweep_debug(direct: bool):
+    """Diagnostics: force the direct-difference gradient sweep (the kernel for d > 24) for every input dimension."""
+    check(_cabi.load().plmc_sweep_debug(int(bool(direct))), "sweep_debug")
+
+
 def trace_enable(on: bool):
     """Per-shape CUDA-event timing of every GEMM of the factorisation layer (diagnostics)."""
     check(_cabi.load().plmc_trace_enable(int(bool(on))), "trace_enable")

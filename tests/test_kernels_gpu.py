@@ -248,6 +248,50 @@ def test_gram_and_cross_gram_vs_oracle(kind, kid, n, d, with_os):
     assert Kx[:, n:, :].abs().max().item() == 0.0 if np_ > n else True
 
 
+@pytest.mark.parametrize("kind,kid", [("rbf", 0), ("matern52", 1), ("matern32", 2)])
+@pytest.mark.parametrize("n,d,with_os", [(100, 1, False), (300, 6, True), (257, 21, False), (640, 12, True),
+                                         (200, 24, False), (150, 30, True)])
+def test_gradient_sweep_both_kernels_vs_autograd(kind, kid, n, d, with_os):
+    """plmc_grad_sweep against torch autograd through the oracle's kernel function, f = sum_ij W_ij K_ij with
+    W = 1/2 (a a^T - Kinv) held fixed: the GEMM-form kernel (d <= 24: distances and A Z on DMMA, two CTAs per SM)
+    and the direct-difference kernel (any d <= 44; forced with plmc_sweep_debug) must both match."""
+    q = 2
+    g = torch.Generator().manual_seed(n * 31 + d)
+    X = torch.rand(n, d, generator=g, dtype=torch.float64) * 2 - 1
+    ell = (torch.rand(q, d, generator=g, dtype=torch.float64) + 0.4).requires_grad_(True)
+    os_ = (torch.rand(q, generator=g, dtype=torch.float64) + 0.5).requires_grad_(True) if with_os else None
+    a = torch.randn(q, n, generator=g, dtype=torch.float64)
+    M = torch.randn(q, n, n, generator=g, dtype=torch.float64)
+    Kinv = M @ M.transpose(1, 2) / n
+    W = 0.5 * (a[:, :, None] * a[:, None, :] - Kinv)
+    f = torch.zeros((), dtype=torch.float64)
+    for l in range(q):
+        Kl = O.base_kernel(kind, X, X, ell[l:l + 1], zero_diag=True)
+        if os_ is not None:
+            Kl = os_[l] * Kl
+        f = f + (W[l] * Kl).sum()
+    f.backward()
+    np_ = ops.npad(n)
+    Xg = X.to(DEV)
+    Z, zn = ops.scale_inputs(Xg, ops.col_mean(Xg), ell.detach().to(DEV), np_)
+    Kp = torch.full((q, np_, np_), float("nan"), dtype=torch.float64, device=DEV)
+    Kp[:, :, :] = torch.eye(np_, dtype=torch.float64, device=DEV)
+    Kp[:, :n, :n] = torch.tril(Kinv).to(DEV) + torch.triu(torch.full((n, n), float("nan"), dtype=torch.float64), 1).to(DEV)
+    ap = torch.zeros((q, np_), dtype=torch.float64, device=DEV)
+    ap[:, :n] = a.to(DEV)
+    osg = None if os_ is None else os_.detach().to(DEV)
+    try:
+        for direct in (False, True):
+            ops.sweep_debug(direct)
+            g_ell, g_os, g_noise = ops.grad_sweep(Kp, ap, Z, zn, ell.detach().to(DEV), kid, osg, n)
+            assert rel_err(g_ell, ell.grad) < 1e-10, (direct, g_ell.cpu(), ell.grad)
+            assert rel_err(g_noise, torch.diagonal(W, dim1=1, dim2=2).sum(-1)) < 1e-12, direct
+            if os_ is not None:
+                assert rel_err(g_os, os_.grad) < 1e-11, direct
+    finally:
+        ops.sweep_debug(False)
+
+
 def test_prediction_epilogues():
     q, n, ns, p = 5, 300, 200, 37
     np_, mt = ops.npad(n), ops.npad(ns)

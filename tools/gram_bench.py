@@ -44,3 +44,7 @@ t = timeit(lambda: ops.gram(Z, zn, kid, None, noise, K, n))
 print(f"gram  n={n} d={d} q={q} kid={kid}: {t:.3f} ms  {bytes_ / t / 1e6:.1f} GB/s")
 t = timeit(lambda: ops.grad_sweep(K, alpha, Z, zn, ell, kid, None, n))
 print(f"sweep n={n} d={d} q={q} kid={kid}: {t:.3f} ms  {bytes_ / t / 1e6:.1f} GB/s")
+ops.sweep_debug(True)
+t = timeit(lambda: ops.grad_sweep(K, alpha, Z, zn, ell, kid, None, n))
+print(f"sweep (direct-difference kernel) n={n} d={d} q={q} kid={kid}: {t:.3f} ms  {bytes_ / t / 1e6:.1f} GB/s")
+ops.sweep_debug(False)
