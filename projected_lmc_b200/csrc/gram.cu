@@ -19,7 +19,6 @@ namespace plmc {
 constexpr int GR_THREADS = 256;
 constexpr int GR_KC = 32;  // input-dimension chunk staged in shared memory by the Gram kernel
 
-__host__ __device__ inline int gram_lds(int dpad) { return ((dpad + 11) / 16) * 16 + 4; }
 
 // xmean[k] = mean_i X[i, k]
 __global__ void __launch_bounds__(256) col_mean_kernel(const double* __restrict__ X, long long n, int d,
@@ -53,18 +52,28 @@ __global__ void __launch_bounds__(256) scale_inputs_kernel(const double* __restr
 
 // MODE 0: training Gram (lower tiles, diagonal noise, identity padding)
 // MODE 1: cross Gram (all tiles; rows >= n are zero)
+// A 128 x 128 tile is processed as two 64-row halves by 8 warps (2 x 4, 32 x 32 entries each): 64 accumulator
+// registers per thread and a 64 KB staging slab, so that TWO CTAs fit an SM for d <= 24 (109 KB, <= 128 registers)
+// and the load / DMMA phase of one overlaps the transcendental phase of the other (ncu of the one-CTA version: FP64
+// pipe 26 % active, 8 warps per SM, top stall "wait").  Wider inputs are staged in chunks of GR_KC dimensions.
+__host__ __device__ inline int gram_kc(int dpad) { return dpad <= 24 ? dpad : GR_KC; }
+__host__ __device__ inline int gram_lds(int kc) { return (kc % 8 == 0) ? kc + 4 : kc + 8; }   // = 4 mod 8
+__host__ __device__ inline size_t gram_smem(int dpad) {
+    return (size_t)(192 * gram_lds(gram_kc(dpad)) + 32 * GR_THREADS) * 8;
+}
+
 template <int KID, int MODE>
-__global__ void __launch_bounds__(GR_THREADS, 1)
+__global__ void __launch_bounds__(GR_THREADS, 2)
     gram_kernel(const double* __restrict__ Zr, const double* __restrict__ znr, long long rows_pad_r,
                 const double* __restrict__ Zc, const double* __restrict__ znc, long long rows_pad_c,
                 const double* __restrict__ os, const double* __restrict__ diag_add, double* __restrict__ Kout,
                 long long ld, long long stride, long long n, int dpad, int tiles_c, int accumulate) {
     extern __shared__ __align__(16) double sm[];
-    const int lds = gram_lds(dpad < GR_KC ? dpad : GR_KC);
-    double* Zi = sm;
-    double* Zj = sm + 128 * lds;
-    double* ni = Zj + 128 * lds;
-    double* nj = ni + 128;
+    const int kcmax = gram_kc(dpad);
+    const int lds = gram_lds(kcmax);
+    double* Zj = sm;                     // [128][lds]
+    double* Zi = Zj + 128 * lds;         // [64][lds]
+    double* stage = Zi + 64 * lds;       // [32][256]: slot e of thread tid at stage[e * 256 + tid]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -84,108 +93,121 @@ __global__ void __launch_bounds__(GR_THREADS, 1)
         tj = blockIdx.x - ti * tiles_c;
     }
     const long long i0 = (long long)ti * 128, j0 = (long long)tj * 128;
-
-    const double* zr = Zr + ((long long)l * rows_pad_r + i0) * dpad;
     const double* zc = Zc + ((long long)l * rows_pad_c + j0) * dpad;
-    if (tid < 128) {
-        ni[tid] = znr[(long long)l * rows_pad_r + i0 + tid];
-        nj[tid] = znc[(long long)l * rows_pad_c + j0 + tid];
-    }
-
-    double acc[8][4][2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    const double* pa = Zi + (wm * 64 + g) * lds + t;
-    const double* pb = Zj + (wn * 32 + g) * lds + t;
-    // input dimensions in chunks of GR_KC columns (shared memory stays bounded for any d)
-    for (int kc0 = 0; kc0 < dpad; kc0 += GR_KC) {
-        const int kc = min(GR_KC, dpad - kc0);
-        __syncthreads();
-        for (int idx = tid; idx < 128 * kc; idx += GR_THREADS) {
-            const int r = idx / kc, k = idx - r * kc;
-            Zi[r * lds + k] = zr[r * dpad + kc0 + k];
-            Zj[r * lds + k] = zc[r * dpad + kc0 + k];
-        }
-        __syncthreads();
-        for (int k0 = 0; k0 < kc; k0 += 4) {
-            double af[8], bf[4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) af[i] = pa[i * 8 * lds + k0];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = pb[j * 8 * lds + k0];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-        }
-    }
-
-    // Stage the squared distances through a private shared-memory slab (slot e of thread tid at
-    // stage[e * 256 + tid]: conflict free, no barrier needed because every thread reads back only
-    // what it wrote).  The transcendental epilogue then runs as a ROLLED loop: fully unrolled it is
-    // ~100 KB of code and the kernel stalls on instruction fetch (ncu: stall_no_instruction 3.4/issue).
-    double* stage = nj + 128;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const double nri = ni[wm * 64 + i * 8 + g];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int cl = wn * 32 + j * 8 + 2 * t;
-            stage[((i * 4 + j) * 2 + 0) * GR_THREADS + tid] = dmax(fma(-2.0, acc[i][j][0], nri + nj[cl]), 0.0);
-            stage[((i * 4 + j) * 2 + 1) * GR_THREADS + tid] = dmax(fma(-2.0, acc[i][j][1], nri + nj[cl + 1]), 0.0);
-        }
-    }
     const double osl = os ? os[l] : 1.0;
     const double dadd = (MODE == 0) ? diag_add[l] : 0.0;
     double* Kl = Kout + (long long)l * stride;
-    // Interior tiles (99 % of them at n = 44k: off the diagonal, no padded row or column) take a loop without any
-    // per-element predicate; diagonal and edge tiles the general one.
-    const bool interior = (MODE == 0) ? (ti != tj && i0 + 128 <= n && j0 + 128 <= n) : (i0 + 128 <= n);
-    if (interior) {
-        double* base = Kl + (i0 + wm * 64 + g) * ld + j0 + wn * 32 + 2 * t;
-#pragma unroll 4
-        for (int pr = 0; pr < 32; ++pr) {
-            const int i = pr >> 2, j = pr & 3;
-            double* dst = base + (long long)(i * 8) * ld + j * 8;
-            double v0 = osl * kernel_value<KID>(stage[(pr * 2 + 0) * GR_THREADS + tid]);
-            double v1 = osl * kernel_value<KID>(stage[(pr * 2 + 1) * GR_THREADS + tid]);
-            if (accumulate) {
-                const double2 old = *reinterpret_cast<const double2*>(dst);
-                v0 += old.x;
-                v1 += old.y;
-            }
-            *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
-        }
-        return;
-    }
-#pragma unroll 4
-    for (int pr = 0; pr < 32; ++pr) {
-        const int i = pr >> 2, j = pr & 3;
-        const long long gi = i0 + wm * 64 + i * 8 + g;
-        const long long gj = j0 + wn * 32 + j * 8 + 2 * t;
-        double v[2];
-        // accumulate: a further component of an additive kernel (sum_g os_g k_g) is added onto the tile; the
-        // noise diagonal and the identity padding were written with the first component
-        double2 old = make_double2(0.0, 0.0);
-        if (accumulate) old = *reinterpret_cast<const double2*>(Kl + gi * ld + gj);
+    const bool single = dpad <= kcmax;   // one chunk: the column side is staged once per tile
+
+    double nj[4][2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const long long gje = gj + e;
-            double s = stage[(pr * 2 + e) * GR_THREADS + tid];
-            if (MODE == 0) {
-                if (gi == gje) s = 0.0;
-                double kv = osl * kernel_value<KID>(s);
-                if (gi == gje && !accumulate) kv += dadd;
-                if (gi >= n || gje >= n) kv = (gi == gje && !accumulate) ? 1.0 : 0.0;
-                v[e] = kv;
-            } else {
-                v[e] = (gi < n) ? osl * kernel_value<KID>(s) : 0.0;
+    for (int j = 0; j < 4; ++j) {
+        const double2 v =
+            __ldg(reinterpret_cast<const double2*>(znc + (long long)l * rows_pad_c + j0 + wn * 32 + j * 8 + 2 * t));
+        nj[j][0] = v.x;
+        nj[j][1] = v.y;
+    }
+
+    for (int h = 0; h < 2; ++h) {
+        const long long ih0 = i0 + 64 * h;
+        const double* zr = Zr + ((long long)l * rows_pad_r + ih0) * dpad;
+        double ni[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ni[i] = __ldg(znr + (long long)l * rows_pad_r + ih0 + wm * 32 + i * 8 + g);
+
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const double* pa = Zi + (wm * 32 + g) * lds + t;
+        const double* pb = Zj + (wn * 32 + g) * lds + t;
+        for (int kc0 = 0; kc0 < dpad; kc0 += kcmax) {
+            const int kc = min(kcmax, dpad - kc0);
+            const int kc2 = kc >> 1;
+            __syncthreads();             // previous readers of Zi (and Zj when it is restaged) are done
+            {
+                const int rr = tid >> 2;
+                const double2* src = reinterpret_cast<const double2*>(zr + rr * dpad + kc0);
+                double2* dst = reinterpret_cast<double2*>(Zi + rr * lds);
+                for (int c = tid & 3; c < kc2; c += 4) dst[c] = __ldg(src + c);
+            }
+            if (!single || h == 0) {
+                const int rr = tid >> 1;
+                const double2* src = reinterpret_cast<const double2*>(zc + rr * dpad + kc0);
+                double2* dst = reinterpret_cast<double2*>(Zj + rr * lds);
+                for (int c = tid & 1; c < kc2; c += 2) dst[c] = __ldg(src + c);
+            }
+            __syncthreads();
+            for (int k0 = 0; k0 < kc; k0 += 4) {
+                double af[4], bf[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) af[i] = pa[i * 8 * lds + k0];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = pb[j * 8 * lds + k0];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
         }
-        *reinterpret_cast<double2*>(Kl + gi * ld + gj) = make_double2(v[0] + old.x, v[1] + old.y);
+
+        // Squared distances into the thread's private slots (conflict free; a thread reads back only what it
+        // wrote, so no barrier), then the transcendental epilogue as a ROLLED loop: fully unrolled it is tens of KB
+        // of code and the kernel stalls on instruction fetch.
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                stage[((i * 4 + j) * 2 + 0) * GR_THREADS + tid] = dmax(fma(-2.0, acc[i][j][0], ni[i] + nj[j][0]), 0.0);
+                stage[((i * 4 + j) * 2 + 1) * GR_THREADS + tid] = dmax(fma(-2.0, acc[i][j][1], ni[i] + nj[j][1]), 0.0);
+            }
+        // Interior half tiles (99 % of them at n = 44k: off the diagonal, no padded row or column) take a loop
+        // without any per-element predicate; diagonal and edge tiles the general one.
+        const bool interior = (MODE == 0) ? (ti != tj && i0 + 128 <= n) : (ih0 + 64 <= n);
+        if (interior) {
+            double* base = Kl + (ih0 + wm * 32 + g) * ld + j0 + wn * 32 + 2 * t;
+#pragma unroll 4
+            for (int pr = 0; pr < 16; ++pr) {
+                const int i = pr >> 2, j = pr & 3;
+                double* dst = base + (long long)(i * 8) * ld + j * 8;
+                double v0 = osl * kernel_value<KID>(stage[(pr * 2 + 0) * GR_THREADS + tid]);
+                double v1 = osl * kernel_value<KID>(stage[(pr * 2 + 1) * GR_THREADS + tid]);
+                if (accumulate) {
+                    const double2 old = *reinterpret_cast<const double2*>(dst);
+                    v0 += old.x;
+                    v1 += old.y;
+                }
+                *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
+            }
+            continue;
+        }
+#pragma unroll 4
+        for (int pr = 0; pr < 16; ++pr) {
+            const int i = pr >> 2, j = pr & 3;
+            const long long gi = ih0 + wm * 32 + i * 8 + g;
+            const long long gj = j0 + wn * 32 + j * 8 + 2 * t;
+            double v[2];
+            // accumulate: a further component of an additive kernel (sum_g os_g k_g) is added onto the tile; the
+            // noise diagonal and the identity padding were written with the first component
+            double2 old = make_double2(0.0, 0.0);
+            if (accumulate) old = *reinterpret_cast<const double2*>(Kl + gi * ld + gj);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const long long gje = gj + e;
+                double s = stage[(pr * 2 + e) * GR_THREADS + tid];
+                if (MODE == 0) {
+                    if (gi == gje) s = 0.0;
+                    double kv = osl * kernel_value<KID>(s);
+                    if (gi == gje && !accumulate) kv += dadd;
+                    if (gi >= n || gje >= n) kv = (gi == gje && !accumulate) ? 1.0 : 0.0;
+                    v[e] = kv;
+                } else {
+                    v[e] = (gi < n) ? osl * kernel_value<KID>(s) : 0.0;
+                }
+            }
+            *reinterpret_cast<double2*>(Kl + gi * ld + gj) = make_double2(v[0] + old.x, v[1] + old.y);
+        }
     }
 }
 
@@ -703,8 +725,7 @@ int plmc_gram(const double* Z, const double* zn, int kernel_id, const double* os
     const long long tm = npad / 128;
     const long long tiles = tm * (tm + 1) / 2;
     if (tiles > 2147483647LL) return PLMC_ERR_BADARG;
-    const size_t smem = (size_t)(2 * 128 * gram_lds(dpad < GR_KC ? dpad : GR_KC) + 256 + 64 * GR_THREADS) * 8;
-    if (smem > 227 * 1024) return PLMC_ERR_BADARG;
+    const size_t smem = gram_smem(dpad);
     return launch_gram<0>(kernel_id, dim3((unsigned)tiles, 1, q), smem, (cudaStream_t)stream, Z, zn, npad, Z, zn, npad,
                           os, diag_add, K, ld, stride, n, dpad, (int)tm, accumulate);
 }
@@ -718,8 +739,7 @@ int plmc_cross_gram(const double* Ztrain, const double* zntrain, const double* Z
         return PLMC_ERR_BADARG;
     const long long tr = npad / 128, tc = mt / 128;
     if (tr * tc > 2147483647LL) return PLMC_ERR_BADARG;
-    const size_t smem = (size_t)(2 * 128 * gram_lds(dpad < GR_KC ? dpad : GR_KC) + 256 + 64 * GR_THREADS) * 8;
-    if (smem > 227 * 1024) return PLMC_ERR_BADARG;
+    const size_t smem = gram_smem(dpad);
     return launch_gram<1>(kernel_id, dim3((unsigned)(tr * tc), 1, q), smem, (cudaStream_t)stream, Ztrain, zntrain,
                           npad, Ztest, zntest, mt_rows_pad, os, nullptr, Kx, ldx, stride, n, dpad, (int)tc, accumulate);
 }
