@@ -516,18 +516,38 @@ def run_train_workload(args, cfg, world, rank, dev):
     params = [prm for prm in model.parameters() if prm.requires_grad]
 
     # optimiser and schedule of the reference's training loop (experiments.py:79-86, 240, 251, 263-273)
-    opt = torch.optim.AdamW(params, lr=1e-2)
-    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=math.exp(math.log(1e-3 / 1e-2) / 10000))
     small = n * n * 8 * q_loc < 200e6
+    gamma = math.exp(math.log(1e-3 / 1e-2) / 10000)
+    # launch-bound workloads on one GPU: the whole iteration as two replayed CUDA graphs, exactly as
+    # projected_lmc_b200.fit runs it (training._GraphedStep); PLMC_BENCH_GRAPH=0 times the eager loop instead
+    use_graph = small and world == 1 and os.environ.get("PLMC_BENCH_GRAPH", "1") != "0"
+    if use_graph:
+        lr_t = torch.tensor(1e-2, dtype=torch.float64, device=dev)
+        opt = torch.optim.AdamW(params, lr=lr_t, capturable=True)
+        sched = None
+    else:
+        lr_t = None
+        opt = torch.optim.AdamW(params, lr=1e-2)
+        sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=gamma)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
+    graphed = {"step": None, "it": 0, "hist": torch.zeros(1 << 16, dtype=torch.float64, device=dev)}
 
     def step():
+        if graphed["step"] is not None:
+            it = graphed["it"] % graphed["hist"].numel()
+            graphed["step"].set_iteration(it)
+            graphed["step"].run(it)
+            graphed["it"] += 1
+            return graphed["step"].loss
         opt.zero_grad(set_to_none=True)
         loss = -mll(model(Xd), Yd)
         loss.backward()
         loss = pdist.allreduce_loss_and_grads(loss, params) if world > 1 else loss.detach()
         opt.step()
-        sched.step()
+        if sched is not None:
+            sched.step()
+        else:
+            lr_t.mul_(gamma)
         return loss
 
     def barrier():
@@ -539,6 +559,11 @@ def run_train_workload(args, cfg, world, rank, dev):
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
+    if use_graph:
+        from projected_lmc_b200.training import _GraphedStep
+
+        graphed["step"] = _GraphedStep(model, mll, Xd, Yd, opt, lr_t, gamma, graphed["hist"], 3)
+        step()                                   # one untimed replay
     peak = dmma_peak_tflops()
     i8_peak = i8_peak_tops()
 
@@ -660,6 +685,9 @@ def run_train_workload(args, cfg, world, rank, dev):
             "predict": predict,
         }
         if small:
+            line["config"]["cuda_graph"] = ("whole iteration replayed as two CUDA graphs (projected_lmc_b200.fit / "
+                                            "training._GraphedStep); the factorisation status is read between them"
+                                            if use_graph else "eager launches")
             line["roofline"]["note"] = ("launch-bound configuration: n=%d gives a %.0f MFLOP factorisation per latent; "
                                         "the step time is kernel-launch latency, not tensor throughput" % (n, n ** 3 / 1e6))
         if not args.no_secondary and not small:

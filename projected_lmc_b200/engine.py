@@ -89,6 +89,8 @@ class LatentEngine:
     # ~130 library launches per iteration at n = 1000 become two graph launches).  Matrices of order <= this are
     # captured after one eager warm-up call; 0 switches it off.
     graph_max_order = int(__import__("os").environ.get("PLMC_GRAPH_MAX_ORDER", "4096"))
+    capture_mode = False     # True while training.fit captures / replays the WHOLE step as a CUDA graph
+    capture_info = None
     max_sweep_dims = 44      # csrc/gram.cu grad_sweep_kernel: (2*128*(dpad+1) + ...)*8 bytes <= 227 KB
     rns_moduli = int(__import__("os").environ.get("PLMC_RNS_MODULI", "16"))
     # precision of the explicit inverse of the training iteration (K^-1 = L^-T L^-1: trtri + lauum).  K^-1 feeds
@@ -241,6 +243,8 @@ class LatentEngine:
         self._mark("gram")
         ops.potrf(K, dinv, info[:q], self.cfg_main)
         info[q:] = (~finite).to(torch.int32)
+        if self.capture_mode:
+            return None
         if self._pinned is None or self._pinned.numel() != q + 1:
             self._pinned = torch.empty((q + 1,), dtype=torch.int32).pin_memory()
         self._pinned.copy_(info, non_blocking=True)
@@ -306,7 +310,8 @@ class LatentEngine:
         q = noise.shape[0]
         ws = self.workspace(X.device, q, n)
         np_ = ws["K"].shape[1]
-        if need_grad and self.profile is None and 0 < np_ <= self.graph_max_order and X.is_cuda:
+        if need_grad and self.profile is None and 0 < np_ <= self.graph_max_order and X.is_cuda \
+                and not self.capture_mode:
             return self._log_prob_and_grads_graphed(ws, X, TY, comps, noise, max_tries)
         mark = self._mark
         mark("start")
@@ -339,6 +344,12 @@ class LatentEngine:
             return lp, (-alpha, g_noise, g_tensors)
 
         out = rest()                      # queued behind the factorisation before its status is known
+        if self.capture_mode:
+            # the caller captures the whole training step into a CUDA graph (training.fit): no host wait in here;
+            # it reads ws["info"] (first bad pivot per latent + the non-finite flag) after every replay and
+            # repeats a failed iteration eagerly, where the jitter retry below applies
+            self.capture_info = ws["info"]
+            return out
         if self._gram_potrf_resolve(ev, ws, comps, scaled, noise, n, max_tries):
             mark("retry")
             out = rest()                  # a jitter retry re-factorised K: redo what depended on it

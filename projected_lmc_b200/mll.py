@@ -23,8 +23,8 @@ def projection_terms(model, S: torch.Tensor, num_data: int):
         if model.log_B_tilde.numel() > 0:
             log_B = model.log_B_tilde
             root_diag = log_B / 2
-            y2 = model.Y_squared_norm if hasattr(model, 'Y_squared_norm') else torch.trace(S)
-            t1 = -0.5 * torch.exp(-log_B[0]) * (y2 - torch.trace(Q.T @ S @ Q)) / num_data
+            y2 = model.Y_squared_norm if hasattr(model, 'Y_squared_norm') else torch.diagonal(S).sum()
+            t1 = -0.5 * torch.exp(-log_B[0]) * (y2 - torch.diagonal(Q.T @ S @ Q).sum()) / num_data
         else:
             t1 = 0.
             root_diag = torch.zeros(1, dtype=S.dtype, device=S.device)
@@ -36,7 +36,7 @@ def projection_terms(model, S: torch.Tensor, num_data: int):
         else:
             Lb = model.B_tilde_inv_chol
             root_diag = -torch.log(torch.diagonal(Lb))
-            t1 = -0.5 * torch.trace(Lb.T @ C @ Lb) / num_data
+            t1 = -0.5 * torch.diagonal(Lb.T @ C @ Lb).sum() / num_data
     t0 = -torch.sum(root_diag)
     if model.lmc_coefficients.bulk:
         t2 = -0.5 * torch.log(torch.diagonal(R) ** 2).sum()

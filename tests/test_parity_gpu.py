@@ -245,6 +245,66 @@ def test_fit_loop_matches_oracle_adamw_trajectory():
     assert out["losses"][-1] < out["losses"][0]
 
 
+@pytest.mark.parametrize("variant,kernel,n", [("PLMC", "matern52", 300), ("PLMC_fast", "rbf", 1100)])
+def test_fit_with_the_whole_step_as_cuda_graphs_follows_the_eager_trajectory(variant, kernel, n):
+    """training.fit(cuda_graph=True): forward + backward (QR of the mixing matrix, projection, Gram, Cholesky,
+    inverse, sweep, projection terms, autograd) replayed as one CUDA graph, AdamW + LR decay as a second one --
+    same loss trajectory and final parameters as the eager loop, and as the oracle's AdamW loop on the CPU."""
+    from projected_lmc_b200 import fit
+
+    X, Y, _, _ = synth(n, 3, 6, 2, seed=n)
+    n_iter, lr, lr_min = 14, 1e-2, 1e-3
+    outs, finals = {}, {}
+    for mode in (False, True):
+        m = make_model(X, Y, 2, variant=variant, kernel=kernel)
+        mc = cpu_copy(m)
+        m = m.cuda()
+        outs[mode] = fit(m, ProjectedLMCmll(m.likelihood, m), m.train_inputs[0], m.train_y, n_iter=n_iter, lr=lr,
+                         lr_min=lr_min, check_every=5, cuda_graph=mode)
+        finals[mode] = [p.detach().cpu().clone() for p in m.parameters()]
+    assert outs[True]["cuda_graph"], outs[True]["cuda_graph_note"]
+    assert not outs[False]["cuda_graph"]
+    assert rel_err(outs[True]["losses"], outs[False]["losses"]) < 1e-10
+    for a, b in zip(finals[True], finals[False]):
+        assert rel_err(a, b) < 1e-7           # capturable AdamW evaluates its bias corrections on the device
+    if n <= 300:
+        opt = torch.optim.AdamW(mc.parameters(), lr=lr)
+        sch = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=float(torch.tensor(lr_min / lr).log().div(n_iter).exp()))
+        ref = []
+        for _ in range(n_iter):
+            opt.zero_grad()
+            loss = -O.mll(oracle_params(mc), X, Y)
+            loss.backward()
+            opt.step()
+            sch.step()
+            ref.append(loss.item())
+        assert rel_err(outs[True]["losses"], torch.tensor(ref)) < 1e-7
+
+
+def test_graphed_fit_repeats_a_failed_factorisation_eagerly_with_jitter():
+    """Duplicated points and a noise floor of e^-40: the factorisation inside the replayed graph fails, the host
+    sees its status between the two graphs and repeats the iteration eagerly (jitter retry) before the optimiser
+    graph runs -- same trajectory as the eager loop."""
+    from projected_lmc_b200 import fit
+
+    X, Y, _, _ = synth(300, 2, 4, 2, seed=77)
+    X[150:] = X[:150]
+    outs = {}
+    for mode in (False, True):
+        m = make_model(X, Y, 2, variant="PLMC", kernel="rbf", perturb=False, noise_thresh=-40.0)
+        with torch.no_grad():
+            m._base_kernel().raw_lengthscale.fill_(3.0)
+            m.likelihood.noise_covar.raw_noise.fill_(-60.0)
+        m = m.cuda()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            outs[mode] = fit(m, ProjectedLMCmll(m.likelihood, m), m.train_inputs[0], m.train_y, n_iter=8, lr=1e-3,
+                             lr_min=None, check_every=4, cuda_graph=mode)
+        assert m._engine.last_jitter is not None and float(m._engine.last_jitter.max()) > 0
+    assert outs[True]["cuda_graph"], outs[True]["cuda_graph_note"]
+    assert rel_err(outs[True]["losses"], outs[False]["losses"]) < 1e-8
+
+
 def test_fit_plateau_stop_rule():
     from projected_lmc_b200 import fit
 
