@@ -55,6 +55,8 @@ extern "C" {
 #define PLMC_GEMM_INT8_DIGITS 1
 #define PLMC_GEMM_INT8_RNS 2
 #define PLMC_GEMM_FLAG_SINGLE_CTA 1 /* RNS: 128x256 single-CTA tiles instead of CTA pairs (diagnostics) */
+#define PLMC_GEMM_FLAG_NO_TRI 4     /* RNS: triangular multiplies (trtri / lauum / trmm) always take the recursion with
+                                       dense 512-leaves instead of one launch set over the nonzero k-tiles (A/B timing) */
 typedef struct plmc_gemm_cfg {
     void* ws;
     long long ws_bytes;
@@ -153,12 +155,14 @@ int plmc_potrf_batched(double* K, long long ld, long long stride, long long npad
 int plmc_trsm_batched(int op, const double* L, long long ld, long long stride, long long npad, int batch,
                       const double* dinv, double* B, long long ldb, long long strideb, long long m, double alpha,
                       const plmc_gemm_cfg* cfg, void* stream);
-/* op 2: B := alpha X B in place, X LOWER triangular [npad, npad] (its strict upper part is not read), B [npad, m],
- * m % 128 == 0: the triangular MULTIPLY the explicit inverse is built from (dense 512-leaves on the tensor path,
- * csrc/linalg.cu).  With X = inv(L) from plmc_trtri_batched it replaces the triangular solve of the predictive
- * variance (gpytorch exact_predictive_covar, reached from projected_lmc.py:1134) at GEMM speed.  dinv: the side
- * buffer of the factorisation calls; its dense-block scratch part is overwritten with copies of X's diagonal
- * blocks.  Other ops: PLMC_ERR_BADARG.                                                                        */
+/* Triangular MULTIPLY in place with a LOWER triangular X [npad, npad] (its strict upper part is not read):
+ *   op 1: B := alpha B X  (B [m, npad])  |  op 2: B := alpha X B  |  op 3: B := X^T B (alpha = 1)   (B [npad, m]),
+ * m % 128 == 0: the products the explicit inverse is built from (csrc/linalg.cu).  In residue mode a large enough
+ * product is ONE launch set whose INT8 GEMM visits only the k-tiles that can be nonzero (csrc/ozaki2.cu rns_trmm);
+ * otherwise a recursion with dense 512-leaves.  With X = inv(L) from plmc_trtri_batched, op 2 replaces the
+ * triangular solve of the predictive variance (gpytorch exact_predictive_covar, reached from projected_lmc.py:1134)
+ * at GEMM speed.  dinv: the side buffer of the factorisation calls; its dense-block scratch part is overwritten
+ * with copies of X's diagonal blocks.  Other ops: PLMC_ERR_BADARG.                                              */
 int plmc_trmm_batched(int op, const double* X, long long ld, long long stride, long long npad, int batch, double* dinv,
                       double* B, long long ldb, long long strideb, long long m, double alpha,
                       const plmc_gemm_cfg* cfg, void* stream);

@@ -147,12 +147,13 @@ int plmc_trsm_batched(int op, const double* L, long long ld, long long stride, l
 int plmc_trmm_batched(int op, const double* X, long long ld, long long stride, long long npad, int batch, double* dinv,
                       double* B, long long ldb, long long strideb, long long m, double alpha,
                       const plmc_gemm_cfg* cfg, void* stream) {
-    if (op != 2 || bad_mat(X, ld, npad, batch) || !dinv || !B || m <= 0 || (m % 128) || (ldb & 1))
+    if (op < 1 || op > 3 || (op == 3 && alpha != 1.0) || bad_mat(X, ld, npad, batch) || !dinv || !B || m <= 0 ||
+        (m % 128) || (ldb & 1))
         return PLMC_ERR_BADARG;
     LaCtx cx;
     if (!make_ctx(cx, (cudaStream_t)stream, batch, cfg)) return PLMC_ERR_BADARG;
-    trmm_lln_lower(cx, BMat{const_cast<double*>(X), ld, stride}, (int)npad, make_dinv(dinv, npad), BMat{B, ldb, strideb},
-                   (int)m, alpha, /*fill_dense=*/true);
+    trmm_lower(cx, op, BMat{const_cast<double*>(X), ld, stride}, (int)npad, make_dinv(dinv, npad), BMat{B, ldb, strideb},
+               (int)m, alpha);
     return cx.status;
 }
 

@@ -109,13 +109,14 @@ void trace_report() {
         cudaEventElapsedTime(&ms, r.e0, r.e1);
         Agg& a = agg[{r.path, r.M, r.N, r.K, r.lower, r.batch}];
         a.count++; a.ms += ms;
-        a.flop += 2.0 * r.M * r.N * r.K * r.batch * (r.lower ? 0.5 : 1.0);
+        a.flop += 2.0 * r.M * r.N * r.K * r.batch * (r.lower ? 0.5 : 1.0) * (r.path == 2 ? 0.5 : 1.0);
         cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
     }
     g_trace_recs.clear();
     fprintf(stderr, "path      M      N      K lower batch   count   total_ms  TFLOP/s\n");
     for (auto& kv : agg)
-        fprintf(stderr, "%-5s %6d %6d %6d %5d %5d %7lld %10.2f %8.1f\n", kv.first[0] ? "int8" : "dmma", kv.first[1],
+        fprintf(stderr, "%-5s %6d %6d %6d %5d %5d %7lld %10.2f %8.1f\n",
+                kv.first[0] == 2 ? "tri" : (kv.first[0] ? "int8" : "dmma"), kv.first[1],
                 kv.first[2], kv.first[3], kv.first[4], kv.first[5], kv.second.count, kv.second.ms,
                 kv.second.flop / kv.second.ms / 1e9);
 }
@@ -263,9 +264,43 @@ static bool dense_leaf(const LaCtx& cx, int M, int N, int K) {
     return gemm_route(cx, M, N, K, false, false, &prec) != 0;
 }
 
+// A product with a lower-triangular operand of order n as ONE residue-plane launch set whose INT8 GEMM visits
+// only the k-tiles that can be nonzero (rns_trmm, csrc/ozaki2.cu) -- instead of the recursion below, which cuts it into
+// n/512 leaf products with K = 512 and updates of every size above that (43-80 TFLOP/s-equivalent at C2 against
+// 150+ for a product that runs its whole inner dimension in one pass).  mode: 1 B X, 2 X B, 3 X^T B, 4 X^T X (lower).
+// Taken in residue mode when the order reaches the residue scheme's minimum inner dimension and the (triangular) work
+// its minimum; returns false when the product should take the recursion (also when the scratch cannot hold it).
+static bool tri_product(LaCtx& cx, int mode, BMat X, int n, BMat B, BMat C, int m, double alpha) {
+    if (cx.oz_mode != 2 || cx.oz_prec <= 0 || (cx.oz_flags & 4)) return false;
+    const int kmin = cx.oz_rns_min_k > BLK ? cx.oz_rns_min_k : BLK;
+    const double work = (mode == 4) ? (double)n * n * n / 3.0 : (double)m * n * n / 2.0;
+    if (n < kmin || (mode != 4 && m < cx.oz_min) || work < (double)cx.oz_rns_min_mnk || work < (double)cx.oz_min_mnk)
+        return false;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_trace) {
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, cx.st);
+    }
+    const int rc = rns_trmm(mode, X.p, X.ld, X.stride, B.p, B.ld, B.stride, C.p, C.ld, C.stride, n, m, alpha, 0.0,
+                            cx.oz_prec, cx.batch, cx.oz_ws, cx.oz_bytes, cx.oz_flags, cx.st);
+    if (g_trace) {
+        if (rc == 0) {
+            cudaEventRecord(e1, cx.st);
+            const int M = (mode == 1) ? m : n, N = (mode == 1 || mode == 4) ? n : m;
+            g_trace_recs.push_back(TraceRec{2, M, N, n, mode == 4 ? 1 : 0, cx.batch, e0, e1});
+        } else {
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
+    }
+    if (rc == 1) return false;      // does not fit the scratch: recurse (the halves will)
+    if (rc != 0) cx.status = rc;
+    return true;
+}
+
 // B := alpha * B * X   (X lower n x n, B m x n)
 static void trmm_rln(LaCtx& cx, BMat X, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha) {
     if (cx.status || n <= 0 || m <= 0) return;
+    if (tri_product(cx, 1, X, n, B, B, m, alpha)) return;
     if (n <= BLK && (blk0 % 4) == 0 && dense_leaf(cx, m, n, n)) {
         gemm(cx, true, false, B, D.dense(blk0), B, m, n, n, alpha, 0.0);
         return;
@@ -284,6 +319,7 @@ static void trmm_rln(LaCtx& cx, BMat X, int n, DinvBuf D, long long blk0, BMat B
 // B := alpha * X * B   (X lower n x n, B n x m)
 static void trmm_lln(LaCtx& cx, BMat X, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha) {
     if (cx.status || n <= 0 || m <= 0) return;
+    if (tri_product(cx, 2, X, n, B, B, m, alpha)) return;
     if (n <= BLK && (blk0 % 4) == 0 && dense_leaf(cx, n, m, n)) {
         gemm(cx, true, false, D.dense(blk0), B, B, n, m, n, alpha, 0.0);
         return;
@@ -339,6 +375,15 @@ void trmm_lln_lower(LaCtx& cx, BMat X, int n, DinvBuf D, BMat B, int m, double a
     trmm_lln(cx, X, n, D, 0, B, m, alpha);
 }
 
+// op 1: B := alpha B X (B m x n) | 2: B := alpha X B | 3: B := X^T B (alpha must be 1)   (B n x m for 2, 3)
+void trmm_lower(LaCtx& cx, int op, BMat X, int n, DinvBuf D, BMat B, int m, double alpha) {
+    if (cx.status || n <= 0 || m <= 0) return;
+    dense_diag_copy(cx, X, n, D, 0);
+    if (op == 1) trmm_rln(cx, X, n, D, 0, B, m, alpha);
+    else if (op == 2) trmm_lln(cx, X, n, D, 0, B, m, alpha);
+    else trmm_llt(cx, X, n, D, 0, B, m);
+}
+
 void trtri_lower(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
     if (cx.status || n <= 0) return;
     trtri_rec(cx, L, n, D, blk0);
@@ -347,6 +392,7 @@ void trtri_lower(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
 // B := T^T B
 void trmm_llt(LaCtx& cx, BMat T, int n, DinvBuf D, long long blk0, BMat B, int m) {
     if (cx.status || n <= 0 || m <= 0) return;
+    if (tri_product(cx, 3, T, n, B, B, m, 1.0)) return;
     if (n <= BLK && (blk0 % 4) == 0 && dense_leaf(cx, n, m, n)) {
         gemm(cx, false, false, D.dense(blk0), B, B, n, m, n, 1.0, 0.0);
         return;
@@ -365,6 +411,7 @@ void trmm_llt(LaCtx& cx, BMat T, int n, DinvBuf D, long long blk0, BMat B, int m
 
 static void lauum_rec(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0) {
     if (cx.status || n <= 0) return;
+    if (tri_product(cx, 4, L, n, L, L, n, 1.0)) return;
     if (n <= BLK && n > LEAF && (blk0 % 4) == 0) {
         // C = T^T T (lower tiles) from the dense copy of the block: operands and result do not alias
         BMat T = D.dense(blk0);

@@ -62,6 +62,12 @@ int rns_gemm(bool aKC, bool bKC, const double* A, long long lda, long long sA, c
              int lower, int nmod, bool same_operand, int batch, void* ws, long long ws_bytes, int flags,
              cudaStream_t st);
 
+// products with a lower-triangular operand X (order n) in one launch set (csrc/ozaki2.cu); returns 1 if the scratch
+// does not hold one batch member (nothing launched), else a PLMC_* status
+int rns_trmm(int mode, const double* X, long long ldx, long long sX, const double* B, long long ldb, long long sB,
+             double* C, long long ldc, long long sC, int n, int m, double alpha, double beta, int nmod, int batch,
+             void* ws, long long ws_bytes, int flags, cudaStream_t st);
+
 // Side buffer of the factorisation layer, per batch member (stride = dinv_elems(npad)):
 //   [0, npad*128)            n/128 consecutive 128x128 row-major blocks holding inv(L_kk) of the 128-leaves
 //                            (upper part explicitly zero), written by potrf;
@@ -99,6 +105,8 @@ void lauum_lower(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, bool fill_
 // B := alpha * X * B  (X lower n x n, B n x m): triangular multiply with dense 512-leaves; fill_dense refreshes
 // the dense copies of X's diagonal blocks in D first (not needed right after trtri_lower on the same matrix)
 void trmm_lln_lower(LaCtx& cx, BMat X, int n, DinvBuf D, BMat B, int m, double alpha, bool fill_dense);
+// op 1: B := alpha B X (B m x n) | 2: B := alpha X B | 3: B := X^T B (alpha = 1)  (B n x m); refreshes the dense copies
+void trmm_lower(LaCtx& cx, int op, BMat X, int n, DinvBuf D, BMat B, int m, double alpha);
 // B := T^T * B  (T lower n x n, B n x m)
 void trmm_llt(LaCtx& cx, BMat T, int n, DinvBuf D, long long blk0, BMat B, int m);
 

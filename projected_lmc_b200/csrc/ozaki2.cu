@@ -239,17 +239,22 @@ __device__ __forceinline__ long long chunk_offset(int x, int k16, int nxt) {
     return ((long long)kt * nxt + xt) * IMG + r * 128 + ((c ^ (r & 7)) << 4);
 }
 
-// KC operand: one warp per row; the row is read twice (absmax, then conversion; the second read hits L2)
+// KC operand: one warp per row; the row is read twice (absmax, then conversion; the second read hits L2).
+// tri = 1: the operand is the LOWER triangle of a square matrix stored in place (entries with k > x are not part of it,
+// whatever the buffer holds there): they are ignored by the row maximum and written as zeros up to the end of the
+// row's 256-aligned diagonal block -- the triangular product (GemmArgs2::tri) never reads k-tiles beyond it.
 __global__ void __launch_bounds__(256) residue_kc_kernel(const double* __restrict__ Pb, long long ld, long long sP,
                                                          int X, int K, int beta, int nmod,
                                                          int8_t* __restrict__ planes_b, long long sPlb, long long sPlm,
-                                                         int nxt, int* __restrict__ ex_b, const ModTab T) {
+                                                         int nxt, int* __restrict__ ex_b, const ModTab T, int tri) {
     const int lane = threadIdx.x & 31;
     const int x = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (x >= X) return;
     const double* row = Pb + (long long)blockIdx.z * sP + (long long)x * ld;
     int8_t* planes = planes_b + (long long)blockIdx.z * sPlb;
     const bool al16 = ((reinterpret_cast<uintptr_t>(row) & 15) == 0);
+    const int kend = tri ? min(K, ((x >> 8) + 1) << 8) : K;      // columns converted
+    const int klast = tri ? x : K - 1;                           // last column that belongs to the operand
     auto load16 = [&](int k16, double (&v)[16]) {
         if (al16) {
 #pragma unroll
@@ -262,11 +267,16 @@ __global__ void __launch_bounds__(256) residue_kc_kernel(const double* __restric
 #pragma unroll
             for (int u = 0; u < 16; ++u) v[u] = row[k16 + u];
         }
+        if (tri && k16 + 15 > klast) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (k16 + u > klast) v[u] = 0.0;
+        }
     };
     // Row maximum: only its binary exponent is needed, and for non-negative doubles the high word orders like the
     // magnitude, so the reduction runs on 32-bit integers (fmax on doubles costs ~7 instructions on sm_100a).
     int hmax = 0;
-    for (int k16 = lane * 16; k16 < K; k16 += 512) {
+    for (int k16 = lane * 16; k16 <= klast; k16 += 512) {
         double v[16];
         load16(k16, v);
 #pragma unroll
@@ -278,9 +288,14 @@ __global__ void __launch_bounds__(256) residue_kc_kernel(const double* __restric
     const int be = hmax >> 20;
     const int e = (hmax == 0) ? 0 : max(be - 1022, -1022);
     if (lane == 0) ex_b[(long long)blockIdx.z * X + x] = e;
-    for (int k16 = lane * 16; k16 < K; k16 += 512) {
+    for (int k16 = lane * 16; k16 < kend; k16 += 512) {
         double v[16];
-        load16(k16, v);
+        if (k16 <= klast) {
+            load16(k16, v);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = 0.0;
+        }
         Digits16 dg;
         dg.set(v, beta - e);
         int8_t* dst = planes + chunk_offset(x, k16, nxt);
@@ -289,18 +304,22 @@ __global__ void __launch_bounds__(256) residue_kc_kernel(const double* __restric
     }
 }
 
-// MC operand, pass 1: exponent of the column-wise absmax over k (integer atomicMax over k-slabs: order independent)
+// MC operand, pass 1: exponent of the column-wise absmax over k (integer atomicMax over k-slabs: order independent).
+// tri = 2: the operand is the LOWER triangle of a square matrix stored in place, indexed (x = column, k = row):
+// entries with k < x are not part of it.
 __global__ void __launch_bounds__(256) absmax_mc_kernel(const double* __restrict__ Pb, long long ld, long long sP,
-                                                        int X, int K, int* __restrict__ ex_b) {
+                                                        int X, int K, int* __restrict__ ex_b, int tri) {
     __shared__ int red[4][64];
     const int xl = threadIdx.x & 63, grp = threadIdx.x >> 6;
     const int x = blockIdx.x * 64 + xl;
     const double* P = Pb + (long long)blockIdx.z * sP;
     int* ex = ex_b + (long long)blockIdx.z * X;
     const int k0 = blockIdx.y * 256, k1 = min(K, k0 + 256);
+    if (tri && k1 <= blockIdx.x * 64) return;   // the whole slab lies above the diagonal
     int emax = -2000000000;
     if (x < X) {
         for (int k = k0 + grp; k < k1; k += 4) {
+            if (tri && k < x) continue;
             const long long bits = __double_as_longlong(P[(long long)k * ld + x]);
             const int be = (int)((bits >> 52) & 0x7FF);
             const int e = be ? be - 1022 : -1022;
@@ -317,21 +336,27 @@ __global__ void __launch_bounds__(256) absmax_mc_kernel(const double* __restrict
 
 // MC operand, pass 2: a (128 k) x (32 x) slab is turned through shared memory (row stride 145, 16-element groups
 // 18 apart: both the transposing stores and the per-thread reads are bank-conflict free); 8 consecutive lanes then
-// write the 128-byte image line of one row.
+// write the 128-byte image line of one row.  tri = 2: entries with k < x become zeros; slabs entirely above the
+// 256-aligned diagonal block of their columns are skipped (the triangular product never reads them).
 __global__ void __launch_bounds__(256) residue_mc_kernel(const double* __restrict__ Pb, long long ld, long long sP,
                                                          int X, int K, int beta, int nmod,
                                                          int8_t* __restrict__ planes_b, long long sPlb, long long sPlm,
-                                                         int nxt, const int* __restrict__ ex_b, const ModTab T) {
+                                                         int nxt, const int* __restrict__ ex_b, const ModTab T,
+                                                         int tri) {
     __shared__ double tile[32 * 145];
     const double* P = Pb + (long long)blockIdx.z * sP;
     int8_t* planes = planes_b + (long long)blockIdx.z * sPlb;
     const int* ex = ex_b + (long long)blockIdx.z * X;
     const int x0 = blockIdx.x * 32, k0 = blockIdx.y * 128;
+    if (tri && k0 + 128 <= ((x0 >> 8) << 8)) return;
     {
         const int xl = threadIdx.x & 31, kr = threadIdx.x >> 5;   // 8 k-rows of 32 x per pass
         double t[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) t[j] = (x0 + xl < X) ? P[(long long)(k0 + kr + 8 * j) * ld + x0 + xl] : 0.0;
+        for (int j = 0; j < 16; ++j) {
+            const int k = k0 + kr + 8 * j;
+            t[j] = (x0 + xl < X && !(tri && k < x0 + xl)) ? P[(long long)k * ld + x0 + xl] : 0.0;
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int k = kr + 8 * j;
@@ -372,6 +397,11 @@ struct GemmArgs2 {
     int nmod;
     int per;                 // work tiles per (batch member, modulus)
     int total;               // per * nmod * batch members of this launch
+    // triangular operand (square, lower, K = its order): only the k-tiles that can be nonzero are visited.
+    //   1: op(A)[m][k] = 0 for k > m (X B)        -> k-tiles [0, end of the row tile's 256-block)
+    //   2: op(A)[m][k] = 0 for k < m (X^T B, X^T X lower) -> k-tiles from the start of the row tile's 256-block
+    //   3: op(B)[k][n] = 0 for k < n (B X)        -> k-tiles from the start of the column tile's 256-block
+    int tri;
     ModTab T;
 };
 
@@ -379,7 +409,7 @@ __host__ __device__ inline long long r_slot(int tm256, int tn256, int ntn256, in
     return lower ? (long long)tm256 * (tm256 + 1) / 2 + tn256 : (long long)tm256 * ntn256 + tn256;
 }
 
-struct WorkTile { int bz, mod, tm, tn; };
+struct WorkTile { int bz, mod, tm, tn, kt0, kt1; };
 template <int CG>
 __device__ __forceinline__ WorkTile decode(const GemmArgs2& p, int w) {
     WorkTile t;
@@ -414,6 +444,11 @@ __device__ __forceinline__ WorkTile decode(const GemmArgs2& p, int w) {
         t.tm = first + r % gsz;
         t.tn = r / gsz;
     }
+    t.kt0 = 0;
+    t.kt1 = p.nkt;
+    if (p.tri == 1) t.kt1 = min(p.nkt, 2 * ((t.tm * CG) >> 1) + 2);
+    else if (p.tri == 2) t.kt0 = 2 * ((t.tm * CG) >> 1);
+    else if (p.tri == 3) t.kt0 = 2 * t.tn;
     return t;
 }
 
@@ -437,8 +472,6 @@ __global__ void __launch_bounds__(THREADS, 1) rns_gemm_kernel(const GemmArgs2 p)
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
     const int cluster_id = blockIdx.x / CG, nclusters = gridDim.x / CG;
     const uint32_t smem0 = (smem_u32(o2_smem) + 1023u) & ~1023u;
-    const int nkt = p.nkt;
-
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::NST; ++i) {
             mbar_init(smem_u32(&full_bar[i]), 1);
@@ -478,7 +511,7 @@ __global__ void __launch_bounds__(THREADS, 1) rns_gemm_kernel(const GemmArgs2 p)
                 const int xb = 2 * t.tn + ((CG == 2) ? (int)rank : 0);
                 const int8_t* ga = p.PA + (long long)t.bz * p.sPAb + (long long)t.mod * p.sPAm + (long long)xa * IMG;
                 const int8_t* gb = p.PB + (long long)t.bz * p.sPBb + (long long)t.mod * p.sPBm + (long long)xb * IMG;
-                for (int kt = 0; kt < nkt; ++kt, ++it) {
+                for (int kt = t.kt0; kt < t.kt1; ++kt, ++it) {
                     const int st = it % C::NST, round = it / C::NST;
                     if (round > 0) mbar_wait<false>(smem_u32(&empty_bar[st]), (round - 1) & 1);
                     const uint32_t fb = smem_u32(&full_bar[st]);
@@ -494,12 +527,13 @@ __global__ void __launch_bounds__(THREADS, 1) rns_gemm_kernel(const GemmArgs2 p)
         const uint32_t idesc = umma_idesc_i8(128 * CG, 256);
         int it = 0, nt = 0;
         for (int w = cluster_id; w < p.total; w += nclusters, ++nt) {
+            const WorkTile t = decode<CG>(p, w);
             const int buf = nt & 1, use = nt >> 1;
             if (use > 0) {   // the epilogue warps (of both CTAs) must have drained this accumulator
                 mbar_wait<false>(smem_u32(&acc_empty[buf]), (use - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
-            for (int kt = 0; kt < nkt; ++kt, ++it) {
+            for (int kt = t.kt0; kt < t.kt1; ++kt, ++it) {
                 const int st = it % C::NST, round = it / C::NST;
                 mbar_wait<false>(smem_u32(&full_bar[st]), round & 1);
                 if (CG == 2) mbar_wait<false>(smem_u32(&peer_full[st]), round & 1);
@@ -510,9 +544,9 @@ __global__ void __launch_bounds__(THREADS, 1) rns_gemm_kernel(const GemmArgs2 p)
 #pragma unroll
                     for (int kk = 0; kk < BK / 32; ++kk)
                         umma_i8<CG>(tmem_base + (uint32_t)buf * 256, umma_desc_sw128(sa + kk * 32),
-                                    umma_desc_sw128(sb + kk * 32), idesc, (kt > 0 || kk > 0) ? 1u : 0u);
+                                    umma_desc_sw128(sb + kk * 32), idesc, (kt > t.kt0 || kk > 0) ? 1u : 0u);
                     umma_commit<CG>(smem_u32(&empty_bar[st]));   // frees the stage (in both CTAs) when the MMAs retire
-                    if (kt == nkt - 1) umma_commit<CG>(smem_u32(&acc_full[buf]));
+                    if (kt == t.kt1 - 1) umma_commit<CG>(smem_u32(&acc_full[buf]));
                 }
                 __syncwarp();
             }
@@ -521,7 +555,8 @@ __global__ void __launch_bounds__(THREADS, 1) rns_gemm_kernel(const GemmArgs2 p)
         // ===== relay (second CTA of the pair): tell the leader when this CTA's stage has landed =====
         int it = 0;
         for (int w = cluster_id; w < p.total; w += nclusters) {
-            for (int kt = 0; kt < nkt; ++kt, ++it) {
+            const WorkTile t = decode<CG>(p, w);
+            for (int kt = t.kt0; kt < t.kt1; ++kt, ++it) {
                 const int st = it % C::NST, round = it / C::NST;
                 mbar_wait<false>(smem_u32(&full_bar[st]), round & 1);
                 if (lane == 0) mbar_arrive_remote(smem_u32(&peer_full[st]), 0);
@@ -814,10 +849,11 @@ long long rns_ws_bytes(int M, int N, int K, int nmod, bool same_operand, bool lo
     return a + b + (long long)nmod * slots * RTILE + round_up(4LL * (M + N), 1024) + 1024;
 }
 
+// tri: GemmArgs2::tri (0 for a plain product); the triangular operand is converted with the matching mask
 static int rns_gemm_fit(bool aKC, bool bKC, const double* A, long long lda, long long sA, const double* B, long long ldb,
                         long long sB, double* Cm, long long ldc, long long sC, int M, int N, int K, double alpha,
                         double beta, int lower, int nmod, bool same_operand, int batch, uint8_t* w0, long long avail,
-                        int flags, cudaStream_t st) {
+                        int flags, cudaStream_t st, int tri = 0) {
     DevAttr* da = nullptr;
     if (int rc = dev_attrs(&da)) return rc;
     const ModTab& T = mod_table();
@@ -841,21 +877,24 @@ static int rns_gemm_fit(bool aKC, bool bKC, const double* A, long long lda, long
         int* ea = (int*)(R + bytesR * bc);
         int* eb = same_operand ? ea : ea + (long long)bc * M;
         auto planes = [&](bool kc, const double* P, long long ld, long long sP, int X, long long Xp, int8_t* pl,
-                          long long bytes, int* ex) {
+                          long long bytes, int* ex, bool masked) {
             const long long sPlm = (long long)K * Xp;
             const int nxt = (int)(Xp / 128);
             if (kc) {
                 residue_kc_kernel<<<dim3((X + 7) / 8, 1, bc), 256, 0, st>>>(P, ld, sP, X, K, bits, nmod, pl, bytes, sPlm,
-                                                                           nxt, ex, T);
+                                                                           nxt, ex, T, masked ? 1 : 0);
             } else {
                 cudaMemsetAsync(ex, 0x80, sizeof(int) * (size_t)X * bc, st);
-                absmax_mc_kernel<<<dim3((X + 63) / 64, (K + 255) / 256, bc), 256, 0, st>>>(P, ld, sP, X, K, ex);
+                absmax_mc_kernel<<<dim3((X + 63) / 64, (K + 255) / 256, bc), 256, 0, st>>>(P, ld, sP, X, K, ex,
+                                                                                          masked ? 2 : 0);
                 residue_mc_kernel<<<dim3((X + 31) / 32, K / 128, bc), 256, 0, st>>>(P, ld, sP, X, K, bits, nmod, pl,
-                                                                                   bytes, sPlm, nxt, ex, T);
+                                                                                   bytes, sPlm, nxt, ex, T,
+                                                                                   masked ? 2 : 0);
             }
         };
-        planes(aKC, A + (long long)b0 * sA, lda, sA, M, Mp, pa, bytesA, ea);
-        if (!same_operand) planes(bKC, B + (long long)b0 * sB, ldb, sB, N, Np, pb, bytesB, eb);
+        // tri 1: A = X (KC, zero for k > m); tri 2: A = X^T (MC, zero for k < m); tri 3: B = X (MC, zero for k < n)
+        planes(aKC, A + (long long)b0 * sA, lda, sA, M, Mp, pa, bytesA, ea, tri == 1 || tri == 2);
+        if (!same_operand) planes(bKC, B + (long long)b0 * sB, ldb, sB, N, Np, pb, bytesB, eb, tri == 3);
         PLMC_CHECK_LAUNCH();
 
         GemmArgs2 g;
@@ -870,6 +909,7 @@ static int rns_gemm_fit(bool aKC, bool bKC, const double* A, long long lda, long
         g.tiles_n = tn256;
         g.m128 = M / 128; g.n128 = N / 128;
         g.lower = lower; g.nmod = nmod;
+        g.tri = tri;
         long long per;
         if (!lower) per = (long long)g.tiles_m * g.tiles_n;
         else if (cg == 2) per = slots;
@@ -1030,6 +1070,41 @@ static int peak_i8(long long iters, int cta_group, double* ops_host, cudaStream_
 int rns_bits(int nmod, int K) { return o2::rns_bits(nmod, K); }
 long long rns_ws_bytes(int M, int N, int K, int nmod, bool same_operand, bool lower) {
     return o2::rns_ws_bytes(M, N, K, nmod, same_operand, lower);
+}
+
+// Products with a LOWER-triangular square operand X (order n, stored in place: whatever lies above its diagonal is
+// ignored) as ONE launch set: planes of both operands, the INT8 product over the k-tiles that can be nonzero only
+// (GemmArgs2::tri), reconstruction.  The recursions of csrc/linalg.cu cut such a product into ~n/512 leaf products
+// with K = 512 and updates of every size down to that; here every output tile runs its full inner dimension in
+// one pass at the rate of a large GEMM, and the flop count is the triangular one (plus the 256-blocks on the diagonal).
+//   mode 1: C[m x n] = alpha B[m x n] X            mode 2: C[n x m] = alpha X B[n x m]
+//   mode 3: C[n x m] = alpha X^T B[n x m]          mode 4: C[n x n] (lower blocks) = alpha X^T X
+// C may alias B (modes 1-3) or X (mode 4): the operands are read into planes before anything is written.
+// Returns 1 (nothing launched) when the scratch does not hold one batch member.
+int rns_trmm(int mode, const double* X, long long ldx, long long sX, const double* B, long long ldb, long long sB,
+             double* C, long long ldc, long long sC, int n, int m, double alpha, double beta, int nmod, int batch,
+             void* ws, long long ws_bytes, int flags, cudaStream_t st) {
+    if (mode < 1 || mode > 4 || nmod < 4 || nmod > o2::MAXMOD || (n % 128) || n <= 0 || batch < 1) return PLMC_ERR_BADARG;
+    if (mode != 4 && ((m % 128) || m <= 0)) return PLMC_ERR_BADARG;
+    if (n > 65536 - 128) return 1;
+    uint8_t* w0 = (uint8_t*)(((uintptr_t)ws + 1023) / 1024 * 1024);
+    const long long avail = ws_bytes - (long long)(w0 - (uint8_t*)ws);
+    const int M = (mode == 1) ? m : n, N = (mode == 1 || mode == 4) ? n : m;
+    if (o2::rns_ws_bytes(M, N, n, nmod, mode == 4, mode == 4) - 1024 > avail) return 1;
+    switch (mode) {
+        case 1:   // A = B_in (m x n, KC), op(B)[k][j] = X[k][j] (MC, zero for k < j)
+            return o2::rns_gemm_fit(true, false, B, ldb, sB, X, ldx, sX, C, ldc, sC, m, n, n, alpha, beta, 0, nmod, false,
+                                    batch, w0, avail, flags, st, 3);
+        case 2:   // A = X (KC, zero for k > i), op(B)[k][j] = B_in[k][j] (MC)
+            return o2::rns_gemm_fit(true, false, X, ldx, sX, B, ldb, sB, C, ldc, sC, n, m, n, alpha, beta, 0, nmod, false,
+                                    batch, w0, avail, flags, st, 1);
+        case 3:   // A = X^T (MC, zero for k < i), op(B) = B_in (MC)
+            return o2::rns_gemm_fit(false, false, X, ldx, sX, B, ldb, sB, C, ldc, sC, n, m, n, alpha, beta, 0, nmod, false,
+                                    batch, w0, avail, flags, st, 2);
+        default:  // X^T X, lower blocks: both operands are the MC planes of X
+            return o2::rns_gemm_fit(false, false, X, ldx, sX, X, ldx, sX, C, ldc, sC, n, n, n, alpha, beta, 1, nmod, true,
+                                    batch, w0, avail, flags, st, 2);
+    }
 }
 
 // C[b] = alpha op(A[b]) op(B[b]) + beta C[b].  A product whose planes and residues do not fit the scratch is

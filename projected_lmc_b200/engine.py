@@ -92,14 +92,20 @@ class LatentEngine:
     capture_mode = False     # True while training.fit captures / replays the WHOLE step as a CUDA graph
     capture_info = None
     max_sweep_dims = 44      # csrc/gram.cu grad_sweep_kernel: (2*128*(dpad+1) + ...)*8 bytes <= 227 KB
-    rns_moduli = int(__import__("os").environ.get("PLMC_RNS_MODULI", "16"))
-    # precision of the explicit inverse of the training iteration (K^-1 = L^-T L^-1: trtri + lauum).  K^-1 feeds
-    # ONLY the gradient sweep tr((alpha alpha^T - K^-1) dK): the loss, alpha and the log-determinant come from L,
-    # which keeps the full precision.  13 moduli = 43-bit operands (K <= 16384): measured against the CPU oracle the
-    # gradients do not move at all down to 12 moduli, even at cond(K) = 2e7 (tools/precision_table.py, DESIGN.md
-    # section 5); tolerance 1e-6.  Saves 3/16 of the INT8 products of those two steps; 0 = same as the main one.
+    # Moduli of the residue-plane products.  The whole O(n^3) layer runs power-capped with the INT8 pipe saturated
+    # (~2.0 POPS at ~850 MHz under the 1000 W cap), so its time is proportional to the number
+    # of INT8 products per FP64 product, i.e. to these two numbers.
+    # Factorisation, solves, prediction: 15 moduli = 50-53 operand bits (plmc_rns_bits), a DGEMM's own rounding level:
+    # at n = 20000, cond ~ 1e8 the loss moves by 6e-13 and the gradients by 4e-11 against 16 moduli, while pure FP64
+    # DMMA arithmetic itself sits 9e-13 / 8e-10 away (tools/kinv_scale_check.py, profiles/r02_moduli_at_scale.jsonl);
+    # tolerances 1e-8 / 1e-6.
+    rns_moduli = int(__import__("os").environ.get("PLMC_RNS_MODULI", "15"))
+    # Explicit inverse of the training iteration (K^-1 = L^-T L^-1: trtri + lauum).  K^-1 feeds ONLY the gradient
+    # sweep tr((alpha alpha^T - K^-1) dK): the loss, alpha and the log-determinant come from L.  12 moduli = 39-42
+    # bits: in the same measurement the gradients move by 4e-12 between 16, 13, 12 and even 11 moduli -- two orders
+    # below the FP64-vs-INT8 difference, five below the tolerance.  0 = same as the main one.
     fp64_slices_kinv = int(__import__("os").environ.get("PLMC_FP64_SLICES_KINV", "6"))
-    rns_moduli_kinv = int(__import__("os").environ.get("PLMC_RNS_MODULI_KINV", "13"))
+    rns_moduli_kinv = int(__import__("os").environ.get("PLMC_RNS_MODULI_KINV", "12"))
     # fp32 grade (models whose tensors are float32; the reference's GPU default, experiments.py:4-8, tolerance 1e-4):
     # storage and accumulation stay FP64, but the operands of the large products carry 32 bits (10 moduli =
     # 10 INT8 products, or 4 digit planes = 10 products) in the factorisation AND the inverse: a third fewer

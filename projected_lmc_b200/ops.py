@@ -106,12 +106,13 @@ def trsm(op: int, L, dinv, B, alpha=1.0, cfg=None):
 
 @_on_device
 def trmm(op: int, X, dinv, B, alpha=1.0, cfg=None):
-    """op 2: B := alpha X B in place for lower-triangular X [batch, npad, npad] (e.g. inv(L) from trtri) and
-    B [batch, npad, m]; the dense-block scratch part of dinv is overwritten."""
+    """In place, X lower triangular [batch, npad, npad] (e.g. inv(L) from trtri): op 1 B := a B X (B [batch, m, npad]),
+    op 2 B := a X B, op 3 B := X^T B (B [batch, npad, m]); the dense-block scratch part of dinv is overwritten."""
     b, np_, _ = X.shape
     check(
         lib().plmc_trmm_batched(
-            op, ptr(X), X.stride(1), X.stride(0), np_, b, ptr(dinv), ptr(B), B.stride(1), B.stride(0), B.shape[2],
+            op, ptr(X), X.stride(1), X.stride(0), np_, b, ptr(dinv), ptr(B), B.stride(1), B.stride(0),
+            B.shape[1] if op == 1 else B.shape[2],
             float(alpha), _cfgp(cfg), stream(),
         ),
         "trmm",

@@ -188,6 +188,14 @@ def test_trmm_with_the_explicit_inverse_equals_the_triangular_solve(mode, prec, 
     assert rel_err(Bs, ref) < 1e-11 and rel_err(Bm, ref) < 1e-11
     with pytest.raises(Exception):
         ops.trmm(0, K, dinv, Bm)
+    # the other two triangular multiplies (B X and X^T B) against dense products with tril(X)
+    Xl = torch.tril(torch.nan_to_num(K, nan=0.0))
+    B1 = rnd(b, m, n, seed=10)
+    ref1 = 0.75 * B1 @ Xl
+    ops.trmm(1, K, dinv, B1, alpha=0.75, cfg=cfg)
+    B3 = B0.clone()
+    ops.trmm(3, K, dinv, B3, cfg=cfg)
+    assert rel_err(B1, ref1) < 1e-12 and rel_err(B3, Xl.transpose(1, 2) @ B0) < 1e-12
 
 
 @pytest.mark.parametrize("n,p,q", [(1, 1, 1), (63, 7, 4), (1000, 50, 10), (4097, 65, 33), (513, 500, 32)])
