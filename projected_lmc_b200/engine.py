@@ -15,6 +15,8 @@ HBM layout (per model, q_local latents of order n, npad = ceil(n/128)*128):
 """
 from __future__ import annotations
 
+import contextlib
+import gc
 import math
 import warnings
 
@@ -23,6 +25,21 @@ import torch
 from . import ops
 from ._cabi import PlmcError, npad as _npad
 from .gp import settings
+
+
+@contextlib.contextmanager
+def no_gc_during_capture():
+    """A cyclic garbage collection that runs while a stream is capturing can destroy an unrelated CUDA graph or
+    free memory of its private pool -- cudaFree / cudaGraphExecDestroy are not allowed then, and the failure is raised
+    inside a destructor (the process aborts).  torch.cuda.graph() collects once BEFORE the capture starts; with the
+    collector switched off for the duration of the capture nothing is destroyed in the middle of it."""
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 class NotPSDError(RuntimeError):
@@ -435,7 +452,7 @@ class LatentEngine:
         torch.cuda.synchronize(dev)
         g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         launches0 = ops.stats_get()[0]
-        with torch.cuda.graph(g1):
+        with no_gc_during_capture(), torch.cuda.graph(g1):
             scaled = self._scaled(X, comps_s, np_)
             finite = torch.isfinite(noise_s).all()
             for (kid, dims, ell, os_), (Z, zn, _, _) in zip(comps_s, scaled):
@@ -445,7 +462,7 @@ class LatentEngine:
             self._gram_all(comps_s, scaled, noise_s, K, n)
             ops.potrf(K, dinv, info[:q], self.cfg_main)
             info[q:] = (~finite).to(torch.int32)
-        with torch.cuda.graph(g2, pool=g1.pool()):
+        with no_gc_during_capture(), torch.cuda.graph(g2, pool=g1.pool()):
             z, alpha, quad, logdet = ops.solve_logdet(K, dinv, TY_s, n, ws["rhs"])
             lp = -0.5 * (quad + logdet + n * math.log(2 * math.pi))
             ops.trtri(K, dinv, self.cfg_kinv)

@@ -19,12 +19,21 @@ iteration; a failed factorisation is repeated eagerly with gpytorch's jitter-ret
 from __future__ import annotations
 
 import time
+import warnings
 from typing import Optional
 
 import numpy as np
 import torch
 
 from . import gp, ops
+from .engine import no_gc_during_capture
+
+
+def _invalidate_data_caches(eng, mll):
+    """Forget everything derived from the contents of X and Y (column means, per-component input subsets, S = Y^T Y)."""
+    eng._xmean_key, eng._xsub = None, {}
+    if hasattr(mll, "_S_key"):
+        mll._S_key = None
 
 
 class _GraphedStep:
@@ -44,9 +53,7 @@ class _GraphedStep:
         optimizer.zero_grad(set_to_none=True)
         # everything derived from X and Y (column means, per-component input subsets, S = Y^T Y) is recomputed INSIDE
         # the graph, so a caller may refresh the contents of X / Y in place between replays
-        self.eng._xmean_key, self.eng._xsub = None, {}
-        if hasattr(mll, "_S_key"):
-            mll._S_key = None
+        _invalidate_data_caches(self.eng, mll)
         # nothing may keep the autograd graph of an earlier (eager) iteration alive: its AccumulateGrad nodes belong
         # to the stream they were created on, and synchronising with that stream is not allowed during capture
         if getattr(mll, "proj_term_list", None) is not None:
@@ -54,14 +61,14 @@ class _GraphedStep:
         self.eng.capture_mode = True
         launches0 = ops.stats_get()[0]
         try:
-            with torch.cuda.graph(self.g1):
+            with no_gc_during_capture(), torch.cuda.graph(self.g1):
                 loss = -mll(model(X), Y)
                 loss.backward()
                 hist.index_copy_(0, self.it_t, loss.detach().reshape(1).to(hist.dtype))
                 self.it_t.add_(1)
             self.loss = loss.detach()
             self.info = self.eng.capture_info
-            with torch.cuda.graph(self.g2, pool=self.g1.pool()):
+            with no_gc_during_capture(), torch.cuda.graph(self.g2, pool=self.g1.pool()):
                 optimizer.step()
                 if lr_t is not None and gamma is not None:
                     lr_t.mul_(gamma)          # ExponentialLR, chained form: lr <- lr * gamma
@@ -142,8 +149,14 @@ def fit(model, mll, X, Y, n_iter: int, lr: float = 1e-2, lr_min: Optional[float]
     start = time.time()
     it = 0
     graphed, graph_note = None, None
-    if can_graph and X.shape == model.train_inputs[0].shape and X.data_ptr() == model.train_inputs[0].data_ptr():
-        X = model.train_inputs[0]              # the identity check of model(X) then needs no device comparison
+    if can_graph and X is not model.train_inputs[0]:
+        # model(X) compares X with the training inputs unless it IS that tensor -- a device comparison with a host
+        # read, which cannot be captured: compare once here and pass the model's own tensor from then on
+        tx = model.train_inputs[0]
+        if X.shape == tx.shape and X.dtype == tx.dtype and (X.data_ptr() == tx.data_ptr() or torch.equal(X, tx)):
+            X = tx
+        else:
+            can_graph = False                  # (the model will refuse these inputs on the first iteration)
     with gp.settings.cholesky_max_tries(cholesky_max_tries):
         for it in range(n_iter):
             if can_graph and graphed is None and it == graph_warmup:
@@ -155,6 +168,17 @@ def fit(model, mll, X, Y, n_iter: int, lr: float = 1e-2, lr_min: Optional[float]
                     can_graph, graph_note = False, repr(ex)[:200]
                     if eng is not None:
                         eng.capture_mode = False
+                        # what the aborted capture cached was recorded, never computed
+                        _invalidate_data_caches(eng, mll)
+                    warnings.warn("the training step could not be captured into a CUDA graph; continuing with eager "
+                                  f"launches ({graph_note})", RuntimeWarning)
+                    try:
+                        # a capture that ended in an error leaves torch's CUDA generator flagged as capturing (every
+                        # later random draw would fail); a trivial successful capture clears the flag
+                        with torch.cuda.graph(torch.cuda.CUDAGraph()):
+                            torch.zeros(1, device=X.device)
+                    except Exception:  # noqa: BLE001
+                        pass
             if graphed is not None:
                 graphed.set_iteration(it) if it == graph_warmup else None
                 graphed.run(it)

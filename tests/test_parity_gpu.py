@@ -305,6 +305,34 @@ def test_graphed_fit_repeats_a_failed_factorisation_eagerly_with_jitter():
     assert rel_err(outs[True]["losses"], outs[False]["losses"]) < 1e-8
 
 
+def test_fit_falls_back_to_eager_launches_when_the_step_cannot_be_captured():
+    """A step with a host read in it cannot be captured: fit() warns, continues eagerly with the same trajectory,
+    and torch's CUDA generator is usable afterwards (a capture that ends in an error leaves it flagged)."""
+    from projected_lmc_b200 import fit
+
+    X, Y, _, _ = synth(200, 2, 4, 2, seed=3)
+    outs = {}
+    for leaky in (False, True):
+        m = make_model(X, Y, 2, variant="PLMC", kernel="rbf").cuda()
+        mll = ProjectedLMCmll(m.likelihood, m)
+        if leaky:
+            orig = mll.forward
+
+            def fwd(*a, _orig=orig, **k):
+                out = _orig(*a, **k)
+                float(out.detach().cpu())                  # host read: not capturable
+                return out
+            mll.forward = fwd
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            outs[leaky] = fit(m, mll, m.train_inputs[0], m.train_y, n_iter=8, lr=1e-3, lr_min=None, cuda_graph=True)
+        if leaky:
+            assert not outs[leaky]["cuda_graph"] and any("could not be captured" in str(x.message) for x in w)
+    assert outs[False]["cuda_graph"]
+    assert rel_err(outs[True]["losses"], outs[False]["losses"]) < 1e-10
+    assert torch.isfinite(torch.randn(4, device="cuda")).all()
+
+
 def test_fit_plateau_stop_rule():
     from projected_lmc_b200 import fit
 
