@@ -462,10 +462,33 @@ def secondary_kernels(model, cfg, n, q_loc, phases, steps, peaks, peak_src):
             e["note"] = note
         out.append(e)
 
-    entry("gram_kernel (fused ARD Gram build, lower tiles written once)", gram_bytes,
-          phases.get("gram", 0.0) / steps * 1e-3)
-    entry("grad_sweep_kernel (fused backward sweep over the lower tiles of K^-1)", gram_bytes,
-          phases.get("grad_sweep", 0.0) / steps * 1e-3)
+    in_step = ("inside the power-capped step (phase events): the FP64 pipe that bounds this kernel runs at the SM clock "
+               "the preceding O(n^3) phases left (~0.8-1.0 GHz of 1.965)")
+    entry("gram_kernel (fused ARD Gram build, lower tiles written once), in the step", gram_bytes,
+          phases.get("gram", 0.0) / steps * 1e-3, in_step)
+    entry("grad_sweep2_kernel (fused backward sweep over the lower tiles of K^-1, GEMM form), in the step", gram_bytes,
+          phases.get("grad_sweep", 0.0) / steps * 1e-3, in_step)
+    # the same two kernels timed alone on the workload's own buffers (burst clocks, as the HBM peak was measured)
+    try:
+        eng = model._engine
+        ws = eng.workspace(model.train_y.device, q_loc, n)
+        X64 = model.train_inputs[0].to(torch.float64)
+        kid = 0 if cfg["kernel"] == "rbf" else 1
+        ell = torch.full((q_loc, cfg["d"]), 0.7, dtype=torch.float64, device=X64.device)
+        noise = torch.full((q_loc,), 0.5, dtype=torch.float64, device=X64.device)
+        Z, zn = ops.scale_inputs(X64, ops.col_mean(X64), ell, np_)
+        alpha = torch.randn(q_loc, np_, dtype=torch.float64, device=X64.device)
+        entry("gram_kernel, timed alone (same shape, workspace of the step)", gram_bytes,
+              timed_calls(lambda: ops.gram(Z, zn, kid, None, noise, ws["K"], n), 3),
+              "FP64-datapath bound, not HBM bound: ncu (profiles/r02_ncu_summary_final.md) FP64 + DMMA pipes 65 % "
+              "busy, top stall math_pipe_throttle; 24 DMMA-FMA + ~29 FP64 instructions per entry against 23 FMA "
+              "slots per entry at the HBM rate")
+        entry("grad_sweep2_kernel, timed alone (same shape; the Gram just written stands in for K^-1)", gram_bytes,
+              timed_calls(lambda: ops.grad_sweep(ws["K"], alpha, Z, zn, ell, kid, None, n), 3),
+              "FP64-datapath bound: two DMMA contractions (48 FMA per entry) + ~40 FP64 instructions per entry")
+        eng.generation += 1
+    except Exception as ex:  # noqa: BLE001
+        out.append({"kernel": "gram / sweep timed alone", "error": repr(ex)[:200]})
     Y = model.train_y.to(torch.float64)          # float32 models: the projection kernels read an FP64 copy
     p = Y.shape[1]
     q = model.n_latents
@@ -473,15 +496,16 @@ def secondary_kernels(model, cfg, n, q_loc, phases, steps, peaks, peak_src):
     T = torch.randn(p, q, dtype=torch.float64, device=dev)
     G = torch.randn(q, n, dtype=torch.float64, device=dev)
     pj = 8.0 * n * (p + q)
-    entry("project_fwd_kernel (workload shape)", pj, timed_calls(lambda: ops.project_fwd(Y, T), 20),
+    entry("project_fwd kernel (workload shape)", pj, timed_calls(lambda: ops.project_fwd(Y, T), 20),
           "Y is %.1f MB: L2-resident and launch-latency bound at this size" % (Y.numel() * 8 / 1e6))
-    entry("project_bwd_kernel + reduce (workload shape)", pj, timed_calls(lambda: ops.project_bwd(Y, G), 20))
+    entry("project_bwd kernel + reduce (workload shape)", pj, timed_calls(lambda: ops.project_bwd(Y, G), 20))
     nb, pb, qb = 4000000, 32, 8                                   # 1.28 GB: streams from HBM
     Yb = torch.randn(nb, pb, dtype=torch.float64, device=dev)
     Tb = torch.randn(pb, qb, dtype=torch.float64, device=dev)
     Gb = torch.randn(qb, nb, dtype=torch.float64, device=dev)
-    entry("project_fwd_kernel (n=4e6, p=32, q=8)", 8.0 * nb * (pb + qb), timed_calls(lambda: ops.project_fwd(Yb, Tb), 5))
-    entry("project_bwd_kernel + reduce (n=4e6, p=32, q=8)", 8.0 * nb * (pb + qb),
+    entry("project_fwd_mma_kernel (n=4e6, p=32, q=8: DMMA, cp.async double-buffered slabs)", 8.0 * nb * (pb + qb),
+          timed_calls(lambda: ops.project_fwd(Yb, Tb), 5))
+    entry("project_bwd_mma_kernel + reduce (n=4e6, p=32, q=8)", 8.0 * nb * (pb + qb),
           timed_calls(lambda: ops.project_bwd(Yb, Gb), 5))
     return out
 

@@ -123,132 +123,204 @@ __global__ void reduce_chunks_kernel(const double* __restrict__ partial, double*
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Streaming versions (the common case: the whole T^T [q, p] fits shared memory, q <= 32, p even).
-// One warp owns 32 consecutive rows of Y at a time: it stages a 32 x 32 slab with 16-byte loads (16 lanes cover
-// the 256 contiguous bytes of a row chunk; with p = 32 the whole slab is one contiguous 8 KB block), then lane r
-// reduces row r against T from shared memory.  No CTA-wide barrier in the loop, Y is read exactly once for all
-// latents, TY is written with full 256-byte lines per latent.
+// Streaming versions (q <= 32, p even, Y 16-byte aligned): both products on the FP64 tensor cores, Y read exactly
+// once with 16-byte asynchronous copies.
+// A warp owns 32 consecutive rows of Y at a time and walks their columns in chunks of 32: each (row block, column
+// chunk) slab is brought into shared memory with cp.async (zero-filled beyond n and p) while the previous slab is
+// multiplied -- two slabs per warp in flight, no CTA-wide barrier in the loop.
+//   forward   TY[l, i] = sum_t T[t, l] Y[i, t]:   A = slab (rows i, k = t),  B[k][n] = T[t][l] read through L1;
+//   backward  dT[t, l] = sum_i Y[i, t] G[l, i]:   A[m][k] = slab^T (m = t, k = i),  B[k][n] = G[l][i] staged beside the slab.
+// Slab row stride 36 doubles (= 4 mod 16): 16-byte aligned rows and conflict-free DMMA fragment reads both ways.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int PS_WARPS = 8;
-constexpr int PS_LD = 33;   // slab row stride (doubles): lane r reading column t hits bank (33 r + t) -> conflict free
+constexpr int PS_WARPS = 4;
+constexpr int PS_LD = 36;
 
-__device__ __forceinline__ void load_slab(const double* __restrict__ Y, long long n, int p, long long r0, int p0,
-                                          int pc, double* slab, int lane) {
-    // 32 rows x 32 columns as 512 double2: k-th load of a lane covers row (k*2 + lane/16), column pair lane%16
-#pragma unroll 4
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src, int src_bytes) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes));
+}
+
+// 32 rows x 32 columns of Y (rows r0.., columns p0..) as 512 16-byte pieces, 16 per lane; pieces outside the matrix
+// are zero-filled (source size 0)
+__device__ __forceinline__ void slab_async(const double* __restrict__ Y, long long n, int p, long long r0, int p0,
+                                           double* slab, int lane) {
+#pragma unroll
     for (int k = 0; k < 16; ++k) {
         const int r = 2 * k + (lane >> 4), c = (lane & 15) * 2;
-        double2 v = make_double2(0.0, 0.0);
         const long long gr = r0 + r;
-        if (gr < n && c < pc) {
-            const double* src = Y + gr * p + p0 + c;
-            if (c + 1 < pc) v = *reinterpret_cast<const double2*>(src);
-            else v.x = src[0];
-        }
-        slab[r * PS_LD + c] = v.x;
-        slab[r * PS_LD + c + 1] = v.y;
+        const bool ok = gr < n && p0 + c < p;           // p is even: a piece is inside or outside as a whole
+        cp_async16(slab + r * PS_LD + c, ok ? Y + gr * p + p0 + c : Y, ok ? 16 : 0);
     }
 }
 
-// TY[l, i] = sum_t T[t, l] Y[i, t];  Tt in shared memory as [q][p] (latent-major: the inner loop walks t)
-__global__ void __launch_bounds__(PS_WARPS * 32) project_fwd_stream_kernel(const double* __restrict__ Y,
-                                                                           const double* __restrict__ T,
-                                                                           double* __restrict__ TY, long long n, int p,
-                                                                           int q, long long ldty) {
+template <int QB>
+__global__ void __launch_bounds__(PS_WARPS * 32) project_fwd_mma_kernel(const double* __restrict__ Y,
+                                                                        const double* __restrict__ T,
+                                                                        double* __restrict__ TY, long long n, int p,
+                                                                        int q, long long ldty) {
     extern __shared__ __align__(16) double psm[];
-    double* Tt = psm;                                  // [q][p]
-    double* slabs = psm + (size_t)q * p;               // [PS_WARPS][32][PS_LD]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int idx = threadIdx.x; idx < p * q; idx += PS_WARPS * 32) {
-        const int t = idx / q, l = idx - t * q;
-        Tt[l * p + t] = T[idx];
-    }
-    __syncthreads();
-    double* slab = slabs + warp * 32 * PS_LD;
+    const int g = lane >> 2, t = lane & 3;
+    double* slabs = psm + warp * 2 * 32 * PS_LD;
     const long long nblk = (n + 31) / 32;
-    for (long long blk = (long long)blockIdx.x * PS_WARPS + warp; blk < nblk; blk += (long long)gridDim.x * PS_WARPS) {
-        const long long r0 = blk * 32;
-        double acc[32];
+    const int nch = (p + 31) / 32;
+    const long long w0 = (long long)blockIdx.x * PS_WARPS + warp, wstride = (long long)gridDim.x * PS_WARPS;
+    if (w0 >= nblk) return;
+    // units = (row block, column chunk) in the order they are consumed; unit u+1 is in flight while u is multiplied
+    long long blk = w0;
+    int ch = 0, buf = 0;
+    slab_async(Y, n, p, blk * 32, 0, slabs, lane);
+    cp_async_commit();
+    double c[4][QB][2];
+    while (blk < nblk) {
+        long long nblk_next = blk;
+        int nch_next = ch + 1;
+        if (nch_next == nch) { nch_next = 0; nblk_next = blk + wstride; }
+        if (nblk_next < nblk) slab_async(Y, n, p, nblk_next * 32, nch_next * 32, slabs + (buf ^ 1) * 32 * PS_LD, lane);
+        cp_async_commit();
+        if (ch == 0) {
 #pragma unroll
-        for (int l = 0; l < 32; ++l) acc[l] = 0.0;
-        for (int p0 = 0; p0 < p; p0 += 32) {
-            const int pc = min(32, p - p0);
-            __syncwarp();
-            load_slab(Y, n, p, r0, p0, pc, slab, lane);
-            __syncwarp();
-            const double* yr = slab + lane * PS_LD;
-            for (int t = 0; t < pc; ++t) {
-                const double y = yr[t];
+            for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
-                for (int l = 0; l < 32; ++l)
-                    if (l < q) acc[l] = fma(y, Tt[l * p + p0 + t], acc[l]);
+                for (int nb = 0; nb < QB; ++nb) c[mb][nb][0] = c[mb][nb][1] = 0.0;
+        }
+        cp_async_wait<1>();
+        __syncwarp();
+        const double* slab = slabs + buf * 32 * PS_LD;
+        const int p0 = ch * 32;
+        const int kend = min(32, ((p - p0 + 3) >> 2) << 2);
+        for (int k0 = 0; k0 < kend; k0 += 4) {
+            double a[4], b[QB];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) a[mb] = slab[(mb * 8 + g) * PS_LD + k0 + t];
+            const int tt = p0 + k0 + t;
+#pragma unroll
+            for (int nb = 0; nb < QB; ++nb) {
+                const int l = nb * 8 + g;
+                b[nb] = (tt < p && l < q) ? __ldg(T + (long long)tt * q + l) : 0.0;
             }
-        }
-        if (r0 + lane < n) {
 #pragma unroll
-            for (int l = 0; l < 32; ++l)
-                if (l < q) TY[(long long)l * ldty + r0 + lane] = acc[l];
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < QB; ++nb) dmma884(c[mb][nb][0], c[mb][nb][1], a[mb], b[nb]);
         }
+        __syncwarp();                                   // everyone is done with this buffer before it is refilled
+        if (ch == nch - 1) {
+            // the consumed buffer is free until the next fetch: turn the accumulator fragments into [latent][row]
+            // there, so that every latent's 32 values leave as one 256-byte line
+            double* stage = slabs + buf * 32 * PS_LD;
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < QB; ++nb) {
+                    stage[(nb * 8 + 2 * t) * PS_LD + mb * 8 + g] = c[mb][nb][0];
+                    stage[(nb * 8 + 2 * t + 1) * PS_LD + mb * 8 + g] = c[mb][nb][1];
+                }
+            __syncwarp();
+            const long long gr = blk * 32 + lane;
+            if (gr < n) {
+                for (int l = 0; l < q; ++l) TY[(long long)l * ldty + gr] = stage[l * PS_LD + lane];
+            }
+            __syncwarp();
+        }
+        blk = nblk_next;
+        ch = nch_next;
+        buf ^= 1;
     }
+    cp_async_wait<0>();
 }
 
-// partial[c, t, l] = sum over the rows of CTA c of Y[i, t] G[l, i]: lane t of a warp accumulates column p0 + t of
-// the slab against the 32 G values of each latent (held one per lane, broadcast by shuffle)
-__global__ void __launch_bounds__(PS_WARPS * 32) project_bwd_stream_kernel(const double* __restrict__ Y,
-                                                                           const double* __restrict__ G, long long ldg,
-                                                                           double* __restrict__ partial, long long n,
-                                                                           int p, int q) {
+// partial[cta, t, l] = sum over the rows of this CTA of Y[i, t] G[l, i]
+template <int QB>
+__global__ void __launch_bounds__(PS_WARPS * 32) project_bwd_mma_kernel(const double* __restrict__ Y,
+                                                                        const double* __restrict__ G, long long ldg,
+                                                                        double* __restrict__ partial, long long n,
+                                                                        int p, int q) {
     extern __shared__ __align__(16) double psm[];
-    double* red = psm;                                  // [PS_WARPS][q][32] per p-chunk reduction buffer
-    double* slabs = psm + (size_t)PS_WARPS * q * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* slab = slabs + warp * 32 * PS_LD;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int SLOT = (32 + QB * 8) * PS_LD;         // Y slab [32][36] followed by the G block [QB*8][36]
+    double* slots = psm + warp * 2 * SLOT;
+    double* red = psm + PS_WARPS * 2 * SLOT;            // [PS_WARPS][32][QB*8] per column chunk
     const long long nblk = (n + 31) / 32;
+    const long long w0 = (long long)blockIdx.x * PS_WARPS + warp, wstride = (long long)gridDim.x * PS_WARPS;
     double* out = partial + (long long)blockIdx.x * p * q;
-    for (int p0 = 0; p0 < p; p0 += 32) {
-        const int pc = min(32, p - p0);
-        double acc[32];
+
+    auto fetch = [&](long long blk, int p0, double* slot) {
+        slab_async(Y, n, p, blk * 32, p0, slot, lane);
+        double* gs = slot + 32 * PS_LD;
+        // G block: QB*8 latents x 32 rows, 8-byte pieces (ldg may be odd), zero-filled outside
 #pragma unroll
-        for (int l = 0; l < 32; ++l) acc[l] = 0.0;
-        for (long long blk = (long long)blockIdx.x * PS_WARPS + warp; blk < nblk;
-             blk += (long long)gridDim.x * PS_WARPS) {
-            const long long r0 = blk * 32;
-            __syncwarp();
-            load_slab(Y, n, p, r0, p0, pc, slab, lane);
-            double g[32];
-#pragma unroll
-            for (int l = 0; l < 32; ++l) g[l] = (l < q && r0 + lane < n) ? G[(long long)l * ldg + r0 + lane] : 0.0;
-            __syncwarp();
-            for (int r = 0; r < 32; ++r) {
-                const double y = slab[r * PS_LD + lane];
-#pragma unroll
-                for (int l = 0; l < 32; ++l)
-                    if (l < q) acc[l] = fma(y, __shfl_sync(0xffffffffu, g[l], r), acc[l]);
-            }
+        for (int k = 0; k < QB * 8; ++k) {
+            const long long gr = blk * 32 + lane;
+            const bool ok = k < q && gr < n;
+            cp_async8(gs + k * PS_LD + lane, ok ? G + (long long)k * ldg + gr : G, ok ? 8 : 0);
         }
-        // fixed-order sum over the 8 warps of the CTA
+    };
+
+    for (int p0 = 0; p0 < p; p0 += 32) {
+        double c[4][QB][2];
 #pragma unroll
-        for (int l = 0; l < 32; ++l)
-            if (l < q) red[(warp * q + l) * 32 + lane] = acc[l];
+        for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < QB; ++nb) c[mb][nb][0] = c[mb][nb][1] = 0.0;
+        int buf = 0;
+        if (w0 < nblk) fetch(w0, p0, slots);
+        cp_async_commit();
+        for (long long blk = w0; blk < nblk; blk += wstride) {
+            if (blk + wstride < nblk) fetch(blk + wstride, p0, slots + (buf ^ 1) * SLOT);
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncwarp();
+            const double* slab = slots + buf * SLOT;
+            const double* gs = slab + 32 * PS_LD;
+#pragma unroll
+            for (int k0 = 0; k0 < 32; k0 += 4) {
+                double a[4], b[QB];
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb) a[mb] = slab[(k0 + t) * PS_LD + mb * 8 + g];   // A[m = column][k = row]
+#pragma unroll
+                for (int nb = 0; nb < QB; ++nb) b[nb] = gs[(nb * 8 + g) * PS_LD + k0 + t];     // B[k = row][n = latent]
+#pragma unroll
+                for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                    for (int nb = 0; nb < QB; ++nb) dmma884(c[mb][nb][0], c[mb][nb][1], a[mb], b[nb]);
+            }
+            __syncwarp();
+            buf ^= 1;
+        }
+        cp_async_wait<0>();
+        // fixed-order sum over the warps of the CTA
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < QB; ++nb) {
+                double* r = red + ((warp * 32 + mb * 8 + g) * (QB * 8) + nb * 8 + 2 * t);
+                r[0] = c[mb][nb][0];
+                r[1] = c[mb][nb][1];
+            }
         __syncthreads();
-        for (int idx = threadIdx.x; idx < q * 32; idx += PS_WARPS * 32) {
-            const int l = idx >> 5, t = idx & 31;
-            if (t < pc) {
+        for (int idx = threadIdx.x; idx < 32 * QB * 8; idx += PS_WARPS * 32) {
+            const int tt = idx / (QB * 8), l = idx - tt * (QB * 8);
+            if (p0 + tt < p && l < q) {
                 double s2 = 0.0;
-                for (int w = 0; w < PS_WARPS; ++w) s2 += red[(w * q + l) * 32 + t];
-                out[(long long)(p0 + t) * q + l] = s2;
+#pragma unroll
+                for (int w = 0; w < PS_WARPS; ++w) s2 += red[(w * 32 + tt) * (QB * 8) + l];
+                out[(long long)(p0 + tt) * q + l] = s2;
             }
         }
         __syncthreads();
     }
 }
 
-static inline bool stream_ok(int p, int q) {
-    return q <= 32 && (p % 2 == 0) && ((size_t)q * p + (size_t)PS_WARPS * 32 * (PS_LD + q)) * 8 <= 200 * 1024;
-}
+static inline bool stream_ok(int p, int q) { return q <= 32 && (p % 2 == 0); }
 static inline int stream_ctas(long long n) {
     const long long need = (n + 32 * PS_WARPS - 1) / (32 * PS_WARPS);
     return (int)(need < 296 ? need : 296);
+}
+static inline size_t fwd_mma_smem() { return (size_t)PS_WARPS * 2 * 32 * PS_LD * 8; }
+static inline size_t bwd_mma_smem(int qb) {
+    return ((size_t)PS_WARPS * 2 * (32 + qb * 8) * PS_LD + (size_t)PS_WARPS * 32 * qb * 8) * 8;
 }
 
 static inline int bwd_chunks(long long n) {
@@ -266,9 +338,22 @@ int plmc_project_fwd(const double* Y, const double* T, double* TY, long long n, 
                      void* stream) {
     if (!Y || !T || !TY || n <= 0 || p <= 0 || q <= 0 || ldty < n) return PLMC_ERR_BADARG;
     if (stream_ok(p, q) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0)) {
-        const size_t smem = ((size_t)q * p + (size_t)PS_WARPS * 32 * PS_LD) * 8;
-        cudaFuncSetAttribute(project_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        project_fwd_stream_kernel<<<stream_ctas(n), PS_WARPS * 32, smem, (cudaStream_t)stream>>>(Y, T, TY, n, p, q, ldty);
+        const size_t smem = fwd_mma_smem();
+        const long long need = (n + 32 * PS_WARPS - 1) / (32 * PS_WARPS);
+        const int ctas = (int)(need < 444 ? need : 444);      // three 74 KB CTAs per SM
+        cudaStream_t st = (cudaStream_t)stream;
+#define PLMC_PFWD(QB)                                                                                               \
+    {                                                                                                               \
+        cudaFuncSetAttribute(project_fwd_mma_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        project_fwd_mma_kernel<QB><<<ctas, PS_WARPS * 32, smem, st>>>(Y, T, TY, n, p, q, ldty);                      \
+    }
+        switch ((q + 7) / 8) {
+            case 1: PLMC_PFWD(1) break;
+            case 2: PLMC_PFWD(2) break;
+            case 3: PLMC_PFWD(3) break;
+            default: PLMC_PFWD(4) break;
+        }
+#undef PLMC_PFWD
         PLMC_CHECK_LAUNCH();
         note_launch(1);
         return PLMC_OK;
@@ -291,12 +376,24 @@ int plmc_project_bwd(const double* Y, const double* G, long long ldg, double* dT
     if (!Y || !G || !dT || !partial || n <= 0 || p <= 0 || q <= 0 || ldg < n) return PLMC_ERR_BADARG;
     if (stream_ok(p, q) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0)) {
         const int ctas = stream_ctas(n);
-        const size_t smem = ((size_t)PS_WARPS * q * 32 + (size_t)PS_WARPS * 32 * PS_LD) * 8;
-        cudaFuncSetAttribute(project_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        project_bwd_stream_kernel<<<ctas, PS_WARPS * 32, smem, (cudaStream_t)stream>>>(Y, G, ldg, partial, n, p, q);
+        const int qb = (q + 7) / 8;
+        const size_t smem = bwd_mma_smem(qb);
+        cudaStream_t st = (cudaStream_t)stream;
+#define PLMC_PBWD(QB)                                                                                               \
+    {                                                                                                               \
+        cudaFuncSetAttribute(project_bwd_mma_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        project_bwd_mma_kernel<QB><<<ctas, PS_WARPS * 32, smem, st>>>(Y, G, ldg, partial, n, p, q);                  \
+    }
+        switch (qb) {
+            case 1: PLMC_PBWD(1) break;
+            case 2: PLMC_PBWD(2) break;
+            case 3: PLMC_PBWD(3) break;
+            default: PLMC_PBWD(4) break;
+        }
+#undef PLMC_PBWD
         PLMC_CHECK_LAUNCH();
         const long long elems = (long long)p * q;
-        reduce_chunks_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, (cudaStream_t)stream>>>(partial, dT, elems, ctas);
+        reduce_chunks_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(partial, dT, elems, ctas);
         PLMC_CHECK_LAUNCH();
         note_launch(2);
         return PLMC_OK;

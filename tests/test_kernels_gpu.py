@@ -198,7 +198,8 @@ def test_trmm_with_the_explicit_inverse_equals_the_triangular_solve(mode, prec, 
     assert rel_err(B1, ref1) < 1e-12 and rel_err(B3, Xl.transpose(1, 2) @ B0) < 1e-12
 
 
-@pytest.mark.parametrize("n,p,q", [(1, 1, 1), (63, 7, 4), (1000, 50, 10), (4097, 65, 33), (513, 500, 32)])
+@pytest.mark.parametrize("n,p,q", [(1, 1, 1), (63, 7, 4), (1000, 50, 10), (4097, 65, 33), (513, 500, 32), (31, 2, 1),
+                                   (777, 6, 3), (5000, 34, 17), (100003, 32, 8), (44484, 8, 4), (20000, 100, 16)])
 def test_projection_fwd_bwd(n, p, q):
     Y, T = rnd(n, p, seed=1), rnd(p, q, seed=2)
     TY = ops.project_fwd(Y, T)
