@@ -123,8 +123,8 @@ __global__ void reduce_chunks_kernel(const double* __restrict__ partial, double*
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Streaming versions (q <= 32, p even, Y 16-byte aligned): both products on the FP64 tensor cores, Y read exactly
-// once with 16-byte asynchronous copies.
+// Streaming versions (q <= 32): both products on the FP64 tensor cores, Y read exactly once with asynchronous copies
+// (16-byte pieces when p is even and Y is 16-byte aligned, 8-byte pieces otherwise).
 // A warp owns 32 consecutive rows of Y at a time and walks their columns in chunks of 32: each (row block, column
 // chunk) slab is brought into shared memory with cp.async (zero-filled beyond n and p) while the previous slab is
 // multiplied -- two slabs per warp in flight, no CTA-wide barrier in the loop.
@@ -142,18 +142,28 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src, 
 
 // 32 rows x 32 columns of Y (rows r0.., columns p0..) as 512 16-byte pieces, 16 per lane; pieces outside the matrix
 // are zero-filled (source size 0)
+template <bool A16>
 __device__ __forceinline__ void slab_async(const double* __restrict__ Y, long long n, int p, long long r0, int p0,
                                            double* slab, int lane) {
+    if (A16) {
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int r = 2 * k + (lane >> 4), c = (lane & 15) * 2;
-        const long long gr = r0 + r;
-        const bool ok = gr < n && p0 + c < p;           // p is even: a piece is inside or outside as a whole
-        cp_async16(slab + r * PS_LD + c, ok ? Y + gr * p + p0 + c : Y, ok ? 16 : 0);
+        for (int k = 0; k < 16; ++k) {
+            const int r = 2 * k + (lane >> 4), c = (lane & 15) * 2;
+            const long long gr = r0 + r;
+            const bool ok = gr < n && p0 + c < p;       // p is even: a piece is inside or outside as a whole
+            cp_async16(slab + r * PS_LD + c, ok ? Y + gr * p + p0 + c : Y, ok ? 16 : 0);
+        }
+    } else {                                            // odd p (or an unaligned Y): 8-byte pieces, one row per step
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const long long gr = r0 + r;
+            const bool ok = gr < n && p0 + lane < p;
+            cp_async8(slab + r * PS_LD + lane, ok ? Y + gr * p + p0 + lane : Y, ok ? 8 : 0);
+        }
     }
 }
 
-template <int QB>
+template <int QB, bool A16>
 __global__ void __launch_bounds__(PS_WARPS * 32) project_fwd_mma_kernel(const double* __restrict__ Y,
                                                                         const double* __restrict__ T,
                                                                         double* __restrict__ TY, long long n, int p,
@@ -169,14 +179,15 @@ __global__ void __launch_bounds__(PS_WARPS * 32) project_fwd_mma_kernel(const do
     // units = (row block, column chunk) in the order they are consumed; unit u+1 is in flight while u is multiplied
     long long blk = w0;
     int ch = 0, buf = 0;
-    slab_async(Y, n, p, blk * 32, 0, slabs, lane);
+    slab_async<A16>(Y, n, p, blk * 32, 0, slabs, lane);
     cp_async_commit();
     double c[4][QB][2];
     while (blk < nblk) {
         long long nblk_next = blk;
         int nch_next = ch + 1;
         if (nch_next == nch) { nch_next = 0; nblk_next = blk + wstride; }
-        if (nblk_next < nblk) slab_async(Y, n, p, nblk_next * 32, nch_next * 32, slabs + (buf ^ 1) * 32 * PS_LD, lane);
+        if (nblk_next < nblk)
+            slab_async<A16>(Y, n, p, nblk_next * 32, nch_next * 32, slabs + (buf ^ 1) * 32 * PS_LD, lane);
         cp_async_commit();
         if (ch == 0) {
 #pragma unroll
@@ -231,7 +242,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32) project_fwd_mma_kernel(const do
 }
 
 // partial[cta, t, l] = sum over the rows of this CTA of Y[i, t] G[l, i]
-template <int QB>
+template <int QB, bool A16>
 __global__ void __launch_bounds__(PS_WARPS * 32) project_bwd_mma_kernel(const double* __restrict__ Y,
                                                                         const double* __restrict__ G, long long ldg,
                                                                         double* __restrict__ partial, long long n,
@@ -247,7 +258,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32) project_bwd_mma_kernel(const do
     double* out = partial + (long long)blockIdx.x * p * q;
 
     auto fetch = [&](long long blk, int p0, double* slot) {
-        slab_async(Y, n, p, blk * 32, p0, slot, lane);
+        slab_async<A16>(Y, n, p, blk * 32, p0, slot, lane);
         double* gs = slot + 32 * PS_LD;
         // G block: QB*8 latents x 32 rows, 8-byte pieces (ldg may be odd), zero-filled outside
 #pragma unroll
@@ -313,7 +324,7 @@ __global__ void __launch_bounds__(PS_WARPS * 32) project_bwd_mma_kernel(const do
     }
 }
 
-static inline bool stream_ok(int p, int q) { return q <= 32 && (p % 2 == 0); }
+static inline bool stream_ok(int p, int q) { return q <= 32 && p > 0; }
 static inline int stream_ctas(long long n) {
     const long long need = (n + 32 * PS_WARPS - 1) / (32 * PS_WARPS);
     return (int)(need < 296 ? need : 296);
@@ -337,16 +348,20 @@ extern "C" {
 int plmc_project_fwd(const double* Y, const double* T, double* TY, long long n, int p, int q, long long ldty,
                      void* stream) {
     if (!Y || !T || !TY || n <= 0 || p <= 0 || q <= 0 || ldty < n) return PLMC_ERR_BADARG;
-    if (stream_ok(p, q) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0)) {
+    if (stream_ok(p, q)) {
+        const bool a16 = (p % 2 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
         const size_t smem = fwd_mma_smem();
         const long long need = (n + 32 * PS_WARPS - 1) / (32 * PS_WARPS);
         const int ctas = (int)(need < 444 ? need : 444);      // three 74 KB CTAs per SM
         cudaStream_t st = (cudaStream_t)stream;
-#define PLMC_PFWD(QB)                                                                                               \
+#define PLMC_PFWD2(QB, A)                                                                                           \
     {                                                                                                               \
-        cudaFuncSetAttribute(project_fwd_mma_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        project_fwd_mma_kernel<QB><<<ctas, PS_WARPS * 32, smem, st>>>(Y, T, TY, n, p, q, ldty);                      \
+        cudaFuncSetAttribute(project_fwd_mma_kernel<QB, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        project_fwd_mma_kernel<QB, A><<<ctas, PS_WARPS * 32, smem, st>>>(Y, T, TY, n, p, q, ldty);                   \
     }
+#define PLMC_PFWD(QB)             \
+    if (a16) PLMC_PFWD2(QB, true) \
+    else PLMC_PFWD2(QB, false)
         switch ((q + 7) / 8) {
             case 1: PLMC_PFWD(1) break;
             case 2: PLMC_PFWD(2) break;
@@ -354,6 +369,7 @@ int plmc_project_fwd(const double* Y, const double* T, double* TY, long long n, 
             default: PLMC_PFWD(4) break;
         }
 #undef PLMC_PFWD
+#undef PLMC_PFWD2
         PLMC_CHECK_LAUNCH();
         note_launch(1);
         return PLMC_OK;
@@ -374,16 +390,20 @@ long long plmc_project_bwd_ws(long long n, int p, int q) {
 int plmc_project_bwd(const double* Y, const double* G, long long ldg, double* dT, double* partial, long long n, int p,
                      int q, void* stream) {
     if (!Y || !G || !dT || !partial || n <= 0 || p <= 0 || q <= 0 || ldg < n) return PLMC_ERR_BADARG;
-    if (stream_ok(p, q) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0)) {
+    if (stream_ok(p, q)) {
+        const bool a16 = (p % 2 == 0) && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
         const int ctas = stream_ctas(n);
         const int qb = (q + 7) / 8;
         const size_t smem = bwd_mma_smem(qb);
         cudaStream_t st = (cudaStream_t)stream;
-#define PLMC_PBWD(QB)                                                                                               \
+#define PLMC_PBWD2(QB, A)                                                                                           \
     {                                                                                                               \
-        cudaFuncSetAttribute(project_bwd_mma_kernel<QB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-        project_bwd_mma_kernel<QB><<<ctas, PS_WARPS * 32, smem, st>>>(Y, G, ldg, partial, n, p, q);                  \
+        cudaFuncSetAttribute(project_bwd_mma_kernel<QB, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        project_bwd_mma_kernel<QB, A><<<ctas, PS_WARPS * 32, smem, st>>>(Y, G, ldg, partial, n, p, q);               \
     }
+#define PLMC_PBWD(QB)             \
+    if (a16) PLMC_PBWD2(QB, true) \
+    else PLMC_PBWD2(QB, false)
         switch (qb) {
             case 1: PLMC_PBWD(1) break;
             case 2: PLMC_PBWD(2) break;
@@ -391,6 +411,7 @@ int plmc_project_bwd(const double* Y, const double* G, long long ldg, double* dT
             default: PLMC_PBWD(4) break;
         }
 #undef PLMC_PBWD
+#undef PLMC_PBWD2
         PLMC_CHECK_LAUNCH();
         const long long elems = (long long)p * q;
         reduce_chunks_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(partial, dT, elems, ctas);
