@@ -55,6 +55,8 @@ extern "C" {
 #define PLMC_GEMM_INT8_DIGITS 1
 #define PLMC_GEMM_INT8_RNS 2
 #define PLMC_GEMM_FLAG_SINGLE_CTA 1 /* RNS: 128x256 single-CTA tiles instead of CTA pairs (diagnostics) */
+#define PLMC_GEMM_FLAG_LEAF_SOLVES 2 /* RNS: the panel solves of potrf recurse to the 128-leaves instead of multiplying
+                                        by the explicit inverses of the diagonal 2048-blocks (diagnostics, A/B timing) */
 #define PLMC_GEMM_FLAG_NO_TRI 4     /* RNS: triangular multiplies (trtri / lauum / trmm) always take the recursion with
                                        dense 512-leaves instead of one launch set over the nonzero k-tiles (A/B timing) */
 typedef struct plmc_gemm_cfg {
@@ -95,7 +97,9 @@ int plmc_trace_report(void);
 long long plmc_npad(long long n);
 /* bytes of the side buffer `dinv` of the factorisation calls for `batch` matrices of order npad: the 128x128
  * inverses of the diagonal Cholesky leaves (written by potrf, read by every solve) followed by ceil(npad/512)
- * slots of 512x512 for zero-padded dense copies of diagonal blocks (scratch of trtri / lauum / potri).        */
+ * slots of 512x512 for zero-padded dense copies of diagonal blocks (scratch of trtri / lauum / potri) and
+ * ceil(npad/2048) slots of 2048x2048 for the explicit inverses of the diagonal 2048-blocks of L that potrf keeps
+ * for its own panel solves in residue mode.                                                                  */
 long long plmc_dinv_bytes(long long npad, int batch);
 
 /* ---- (1) projection: ProjectedGPModel.project_data, projected_lmc.py:1014-1021

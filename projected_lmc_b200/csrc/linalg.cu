@@ -47,11 +47,26 @@ static int leaf_attr() {
 // triangular multiplies treat as a dense leaf starts on a 512 boundary (its zero-padded copy has a fixed slot in
 // the side buffer); at and below 512 the cut is at a multiple of the 128-leaf.
 static inline int split128(int n) {
+    if (n > PB) {   // ... and above 2048 at a multiple of 2048 (the blocks whose inverses the panel solves of potrf use)
+        const int k = n / PB;
+        return (k >= 2) ? (k / 2) * PB : PB;
+    }
     if (n > BLK) {
         const int k = n / BLK;
         return (k >= 2) ? (k / 2) * BLK : BLK;
     }
     return ((n / LEAF) / 2) * LEAF;
+}
+
+// lower part of an n x n block (n <= 2048) -> its slot (row stride 2048), zeros above the diagonal
+__global__ void tril_copy_kernel(const double* __restrict__ Lbase, long long ld, long long sL,
+                                 double* __restrict__ Dbase, long long sD, int n) {
+    const int b = blockIdx.z;
+    const double* L = Lbase + (long long)b * sL;
+    double* D = Dbase + (long long)b * sD;
+    const int r = blockIdx.y;
+    for (int c = threadIdx.x + blockIdx.x * blockDim.x; c < n; c += blockDim.x * gridDim.x)
+        D[(long long)r * PB + c] = (c <= r) ? L[(long long)r * ld + c] : 0.0;
 }
 
 // lower part of each diagonal 512-block of L (zero above the diagonal, zero padding up to 512) -> its dense slot
@@ -168,7 +183,11 @@ static void gemm_impl(LaCtx& cx, bool aKC, bool bKC, BMat A, BMat B, BMat C, int
     cx.status = gemm_launch(aKC, bKC, g, cx.batch, cx.st);
 }
 
-void potrf_lower(LaCtx& cx, BMat A, int n, DinvBuf D, long long blk0, int* info) {
+static void trtri_rec(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0);
+static bool tri_product(LaCtx& cx, int mode, BMat X, int n, BMat B, BMat C, int m, double alpha);
+
+// blocks of order <= 2048: the plain recursion (solves against 128-leaves)
+static void potrf_rec(LaCtx& cx, BMat A, int n, DinvBuf D, long long blk0, int* info) {
     if (cx.status || n <= 0) return;
     if (n == LEAF) {
         if ((cx.status = leaf_attr())) return;
@@ -181,11 +200,60 @@ void potrf_lower(LaCtx& cx, BMat A, int n, DinvBuf D, long long blk0, int* info)
     }
     const int n1 = split128(n), n2 = n - n1;
     BMat A11 = A, A21 = A.sub(n1, 0), A22 = A.sub(n1, n1);
-    potrf_lower(cx, A11, n1, D, blk0, info);
+    potrf_rec(cx, A11, n1, D, blk0, info);
     trsm_rlt(cx, A11, n1, D, blk0, A21, n2, 1.0);
     // A22 -= A21 * A21^T   (lower tiles only)
     gemm(cx, true, true, A21, A21, A22, n2, n2, n1, -1.0, 1.0, /*lower=*/1);
-    potrf_lower(cx, A22, n2, D, blk0 + n1 / LEAF, info);
+    potrf_rec(cx, A22, n2, D, blk0 + n1 / LEAF, info);
+}
+
+// Panel solve of the factorisation, X L^T = alpha B.  In residue mode potrf keeps the explicit inverse of every
+// diagonal 2048-block of L it has finished (side buffer, D.panel): the solve against such a block is then ONE
+// triangular product X = alpha B inv(L_kk)^T on the tensor path (rns_trmm mode 5) instead of a recursion to sixteen
+// 128-leaf products and fifteen updates with K = 128 ... 1024, which ran at 4-56 TFLOP/s-equivalent and made up
+// ~400 ms of the C2 iteration.  Between the blocks the update B2 -= X1 L21^T is a plain GEMM as before.
+static bool panel_inverses(const LaCtx& cx) { return cx.oz_mode == 2 && cx.oz_prec > 0 && !(cx.oz_flags & 2); }
+
+static void trsm_panel(LaCtx& cx, BMat L, int n, DinvBuf D, long long blk0, BMat B, int m, double alpha) {
+    if (cx.status || n <= 0 || m <= 0) return;
+    if (n <= PB) {
+        if (n == PB && (blk0 % 16) == 0 && panel_inverses(cx) && tri_product(cx, 5, D.panel(blk0), n, B, B, m, alpha))
+            return;
+        trsm_rlt(cx, L, n, D, blk0, B, m, alpha);
+        return;
+    }
+    const int n1 = split128(n), n2 = n - n1;
+    BMat B1 = B, B2 = B.sub(0, n1);
+    trsm_panel(cx, L, n1, D, blk0, B1, m, alpha);
+    gemm(cx, true, true, B1, L.sub(n1, 0), B2, m, n2, n1, -1.0, alpha);
+    trsm_panel(cx, L.sub(n1, n1), n2, D, blk0 + n1 / LEAF, B2, m, 1.0);
+}
+
+// need_inv: some panel solve further up will use the inverse of the diagonal 2048-blocks of this part
+static void potrf_top(LaCtx& cx, BMat A, int n, DinvBuf D, long long blk0, int* info, bool need_inv) {
+    if (cx.status || n <= 0) return;
+    if (n <= PB) {
+        potrf_rec(cx, A, n, D, blk0, info);
+        if (need_inv && n == PB && (blk0 % 16) == 0 && panel_inverses(cx) && !cx.status) {
+            BMat T = D.panel(blk0);
+            tril_copy_kernel<<<dim3(4, n, cx.batch), 256, 0, cx.st>>>(A.p, A.ld, A.stride, T.p, T.stride, n);
+            if (cudaGetLastError() != cudaSuccess) { cx.status = PLMC_ERR_LAUNCH; return; }
+            note_launch(1);
+            trtri_rec(cx, T, n, D, blk0);       // (a failed pivot leaves garbage here as in L: info tells the caller)
+        }
+        return;
+    }
+    const int n1 = split128(n), n2 = n - n1;
+    BMat A11 = A, A21 = A.sub(n1, 0), A22 = A.sub(n1, n1);
+    potrf_top(cx, A11, n1, D, blk0, info, true);
+    trsm_panel(cx, A11, n1, D, blk0, A21, n2, 1.0);
+    // A22 -= A21 * A21^T   (lower tiles only)
+    gemm(cx, true, true, A21, A21, A22, n2, n2, n1, -1.0, 1.0, /*lower=*/1);
+    potrf_top(cx, A22, n2, D, blk0 + n1 / LEAF, info, need_inv);
+}
+
+void potrf_lower(LaCtx& cx, BMat A, int n, DinvBuf D, long long blk0, int* info) {
+    potrf_top(cx, A, n, D, blk0, info, false);
 }
 
 // X L^T = alpha B ;  L^T = [[L11^T, L21^T],[0, L22^T]]
@@ -270,12 +338,15 @@ static bool dense_leaf(const LaCtx& cx, int M, int N, int K) {
 // 150+ for a product that runs its whole inner dimension in one pass).  mode: 1 B X, 2 X B, 3 X^T B, 4 X^T X (lower).
 // Taken in residue mode when the order reaches the residue scheme's minimum inner dimension and the (triangular) work
 // its minimum; returns false when the product should take the recursion (also when the scratch cannot hold it).
+// mode 5: B X^T (the panel solve of potrf with X = the inverse of a diagonal block).
 static bool tri_product(LaCtx& cx, int mode, BMat X, int n, BMat B, BMat C, int m, double alpha) {
     if (cx.oz_mode != 2 || cx.oz_prec <= 0 || (cx.oz_flags & 4)) return false;
     const int kmin = cx.oz_rns_min_k > BLK ? cx.oz_rns_min_k : BLK;
     const double work = (mode == 4) ? (double)n * n * n / 3.0 : (double)m * n * n / 2.0;
-    if (n < kmin || (mode != 4 && m < cx.oz_min) || work < (double)cx.oz_rns_min_mnk || work < (double)cx.oz_min_mnk)
-        return false;
+    // mode 5 (panel solve of potrf): the alternative is a solve recursion, not a digit-plane GEMM -- a quarter of the
+    // residue scheme's work floor is enough
+    const double floor_rns = (mode == 5) ? (double)cx.oz_rns_min_mnk * 0.25 : (double)cx.oz_rns_min_mnk;
+    if (n < kmin || (mode != 4 && m < cx.oz_min) || work < floor_rns || work < (double)cx.oz_min_mnk) return false;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_trace) {
         cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -286,7 +357,7 @@ static bool tri_product(LaCtx& cx, int mode, BMat X, int n, BMat B, BMat C, int 
     if (g_trace) {
         if (rc == 0) {
             cudaEventRecord(e1, cx.st);
-            const int M = (mode == 1) ? m : n, N = (mode == 1 || mode == 4) ? n : m;
+            const int M = (mode == 1 || mode == 5) ? m : n, N = (mode == 1 || mode == 4 || mode == 5) ? n : m;
             g_trace_recs.push_back(TraceRec{2, M, N, n, mode == 4 ? 1 : 0, cx.batch, e0, e1});
         } else {
             cudaEventDestroy(e0); cudaEventDestroy(e1);

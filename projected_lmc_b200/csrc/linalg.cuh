@@ -74,18 +74,29 @@ int rns_trmm(int mode, const double* X, long long ldx, long long sX, const doubl
 //   [npad*128, ...)          ceil(npad/512) slots of 512x512: zero-padded DENSE copies of the diagonal 512-blocks of
 //                            the triangular matrix being multiplied (trtri / lauum), so that the leaf of a
 //                            triangular multiply is one K = 512 GEMM on the tensor path instead of a 128-recursion.
+//   [.., ...)                ceil(npad/2048) slots of 2048x2048: explicit inverses of the diagonal 2048-blocks of L,
+//                            written by potrf as it goes (residue mode): the panel solve against such a block is ONE
+//                            triangular product on the tensor path instead of a solve recursion to the 128-leaves.
 constexpr int BLK = 512;
-__host__ inline long long dinv_elems(long long npad) { return npad * 128 + ((npad + BLK - 1) / BLK) * (long long)BLK * BLK; }
+constexpr int PB = 2048;
+__host__ inline long long dinv_elems(long long npad) {
+    return npad * 128 + ((npad + BLK - 1) / BLK) * (long long)BLK * BLK + ((npad + PB - 1) / PB) * (long long)PB * PB;
+}
 struct DinvBuf {
     double* p;
     long long stride;
     long long dense_off;   // npad * 128
+    long long panel_off;   // dense_off + ceil(npad/512) * 512^2
     __host__ BMat leaf(long long blk) const { return BMat{p + blk * 16384, 128, stride}; }
     // dense copy of the 512-block that starts at 128-leaf index blk (blk % 4 == 0)
     __host__ BMat dense(long long blk) const { return BMat{p + dense_off + (blk / 4) * (long long)BLK * BLK, BLK, stride}; }
+    // inverse of the diagonal 2048-block that starts at 128-leaf index blk (blk % 16 == 0)
+    __host__ BMat panel(long long blk) const { return BMat{p + panel_off + (blk / 16) * (long long)PB * PB, PB, stride}; }
 };
 __host__ inline DinvBuf make_dinv(const double* dinv, long long npad) {
-    return DinvBuf{const_cast<double*>(dinv), dinv_elems(npad), npad * 128};
+    const long long dense_off = npad * 128;
+    return DinvBuf{const_cast<double*>(dinv), dinv_elems(npad), dense_off,
+                   dense_off + ((npad + BLK - 1) / BLK) * (long long)BLK * BLK};
 }
 
 // A (lower) -> L in place; info[b] = 0 or 1-based index of first non-positive pivot.

@@ -401,6 +401,7 @@ struct GemmArgs2 {
     //   1: op(A)[m][k] = 0 for k > m (X B)        -> k-tiles [0, end of the row tile's 256-block)
     //   2: op(A)[m][k] = 0 for k < m (X^T B, X^T X lower) -> k-tiles from the start of the row tile's 256-block
     //   3: op(B)[k][n] = 0 for k < n (B X)        -> k-tiles from the start of the column tile's 256-block
+    //   4: op(B)[k][n] = 0 for k > n (B X^T)      -> k-tiles [0, end of the column tile's 256-block)
     int tri;
     ModTab T;
 };
@@ -449,6 +450,7 @@ __device__ __forceinline__ WorkTile decode(const GemmArgs2& p, int w) {
     if (p.tri == 1) t.kt1 = min(p.nkt, 2 * ((t.tm * CG) >> 1) + 2);
     else if (p.tri == 2) t.kt0 = 2 * ((t.tm * CG) >> 1);
     else if (p.tri == 3) t.kt0 = 2 * t.tn;
+    else if (p.tri == 4) t.kt1 = min(p.nkt, 2 * t.tn + 2);
     return t;
 }
 
@@ -892,9 +894,10 @@ static int rns_gemm_fit(bool aKC, bool bKC, const double* A, long long lda, long
                                                                                    masked ? 2 : 0);
             }
         };
-        // tri 1: A = X (KC, zero for k > m); tri 2: A = X^T (MC, zero for k < m); tri 3: B = X (MC, zero for k < n)
+        // tri 1: A = X (KC, zero for k > m); tri 2: A = X^T (MC, zero for k < m); tri 3: B = X (MC, zero for k < n);
+        // tri 4: B = X^T, i.e. planes (n, k) = X[n][k] (KC, zero for k > n)
         planes(aKC, A + (long long)b0 * sA, lda, sA, M, Mp, pa, bytesA, ea, tri == 1 || tri == 2);
-        if (!same_operand) planes(bKC, B + (long long)b0 * sB, ldb, sB, N, Np, pb, bytesB, eb, tri == 3);
+        if (!same_operand) planes(bKC, B + (long long)b0 * sB, ldb, sB, N, Np, pb, bytesB, eb, tri == 3 || tri == 4);
         PLMC_CHECK_LAUNCH();
 
         GemmArgs2 g;
@@ -1079,17 +1082,18 @@ long long rns_ws_bytes(int M, int N, int K, int nmod, bool same_operand, bool lo
 // one pass at the rate of a large GEMM, and the flop count is the triangular one (plus the 256-blocks on the diagonal).
 //   mode 1: C[m x n] = alpha B[m x n] X            mode 2: C[n x m] = alpha X B[n x m]
 //   mode 3: C[n x m] = alpha X^T B[n x m]          mode 4: C[n x n] (lower blocks) = alpha X^T X
+//   mode 5: C[m x n] = alpha B[m x n] X^T
 // C may alias B (modes 1-3) or X (mode 4): the operands are read into planes before anything is written.
 // Returns 1 (nothing launched) when the scratch does not hold one batch member.
 int rns_trmm(int mode, const double* X, long long ldx, long long sX, const double* B, long long ldb, long long sB,
              double* C, long long ldc, long long sC, int n, int m, double alpha, double beta, int nmod, int batch,
              void* ws, long long ws_bytes, int flags, cudaStream_t st) {
-    if (mode < 1 || mode > 4 || nmod < 4 || nmod > o2::MAXMOD || (n % 128) || n <= 0 || batch < 1) return PLMC_ERR_BADARG;
+    if (mode < 1 || mode > 5 || nmod < 4 || nmod > o2::MAXMOD || (n % 128) || n <= 0 || batch < 1) return PLMC_ERR_BADARG;
     if (mode != 4 && ((m % 128) || m <= 0)) return PLMC_ERR_BADARG;
     if (n > 65536 - 128) return 1;
     uint8_t* w0 = (uint8_t*)(((uintptr_t)ws + 1023) / 1024 * 1024);
     const long long avail = ws_bytes - (long long)(w0 - (uint8_t*)ws);
-    const int M = (mode == 1) ? m : n, N = (mode == 1 || mode == 4) ? n : m;
+    const int M = (mode == 1 || mode == 5) ? m : n, N = (mode == 1 || mode == 4 || mode == 5) ? n : m;
     if (o2::rns_ws_bytes(M, N, n, nmod, mode == 4, mode == 4) - 1024 > avail) return 1;
     switch (mode) {
         case 1:   // A = B_in (m x n, KC), op(B)[k][j] = X[k][j] (MC, zero for k < j)
@@ -1101,6 +1105,9 @@ int rns_trmm(int mode, const double* X, long long ldx, long long sX, const doubl
         case 3:   // A = X^T (MC, zero for k < i), op(B) = B_in (MC)
             return o2::rns_gemm_fit(false, false, X, ldx, sX, B, ldb, sB, C, ldc, sC, n, m, n, alpha, beta, 0, nmod, false,
                                     batch, w0, avail, flags, st, 2);
+        case 5:   // A = B_in (m x n, KC), op(B)[k][j] = X[j][k]: the KC planes of X (zero for k > j)
+            return o2::rns_gemm_fit(true, true, B, ldb, sB, X, ldx, sX, C, ldc, sC, m, n, n, alpha, beta, 0, nmod, false,
+                                    batch, w0, avail, flags, st, 4);
         default:  // X^T X, lower blocks: both operands are the MC planes of X
             return o2::rns_gemm_fit(false, false, X, ldx, sX, X, ldx, sX, C, ldc, sC, n, n, n, alpha, beta, 1, nmod, true,
                                     batch, w0, avail, flags, st, 2);

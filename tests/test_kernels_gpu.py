@@ -123,6 +123,36 @@ def test_inverse_with_dense_512_leaves_on_the_tensor_path(mode, prec, n):
     assert torch.equal(torch.tril(K2), torch.tril(K))
 
 
+@pytest.mark.parametrize("n", [6144, 4736])          # 3 x 2048, and 2 x 2048 + 640 (ragged last block)
+def test_potrf_panel_solves_through_the_inverses_of_the_diagonal_2048_blocks(n):
+    """Residue mode, default routing thresholds: the panel solve below a finished diagonal 2048-block is one
+    triangular product with the block's explicit inverse (rns_trmm mode 5).  Same factor as torch's Cholesky, same
+    solves / inverse afterwards, and the diagnostic flag that restores the 128-leaf solves agrees to rounding."""
+    b = 2
+    K0 = spd(b, n, seed=n)
+    Lref = torch.linalg.cholesky(K0)
+    ws = torch.empty(6 << 30, dtype=torch.uint8, device=DEV)
+    out = {}
+    for flags in (0, 2):
+        cfg = ops.gemm_cfg(ws, ops.GEMM_INT8_RNS, 15, min_dim=128, flags=flags, alt_precision=7, rns_min_k=1024,
+                           rns_min_mnk=int(2e10), min_mnk=512 ** 3)
+        K = K0.clone()
+        dinv = ops.alloc_dinv(n, b, DEV)
+        info = torch.zeros(b, dtype=torch.int32, device=DEV)
+        ops.potrf(K, dinv, info, cfg)
+        assert info.tolist() == [0] * b
+        out[flags] = torch.tril(K).clone()
+        assert rel_err(out[flags], Lref) < 1e-12, flags
+        y = rnd(b, n, seed=3)
+        z, alpha, quad, logdet = ops.solve_logdet(K, dinv, y, n)
+        zref = torch.linalg.solve_triangular(Lref, y.unsqueeze(-1), upper=False)
+        aref = torch.linalg.solve_triangular(Lref.transpose(1, 2), zref, upper=True).squeeze(-1)
+        assert rel_err(alpha, aref) < 1e-10
+        ops.potri(K, dinv, cfg)
+        assert rel_err(torch.tril(K), torch.tril(torch.linalg.inv(K0))) < 1e-9
+    assert rel_err(out[0], out[2]) < 1e-13
+
+
 def test_potrf_reports_first_bad_pivot_per_batch_member():
     n = 384
     K = spd(3, n, seed=2)
