@@ -98,8 +98,8 @@ long long plmc_npad(long long n);
 /* bytes of the side buffer `dinv` of the factorisation calls for `batch` matrices of order npad: the 128x128
  * inverses of the diagonal Cholesky leaves (written by potrf, read by every solve) followed by ceil(npad/512)
  * slots of 512x512 for zero-padded dense copies of diagonal blocks (scratch of trtri / lauum / potri) and
- * ceil(npad/2048) slots of 2048x2048 for the explicit inverses of the diagonal 2048-blocks of L that potrf keeps
- * for its own panel solves in residue mode.                                                                  */
+ * (npad > 2048) ceil(npad/2048) slots of 2048x2048 for the explicit inverses of the diagonal 2048-blocks of L that
+ * potrf keeps for its own panel solves in residue mode.                                                                */
 long long plmc_dinv_bytes(long long npad, int batch);
 
 /* ---- (1) projection: ProjectedGPModel.project_data, projected_lmc.py:1014-1021

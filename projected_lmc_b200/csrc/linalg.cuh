@@ -79,8 +79,9 @@ int rns_trmm(int mode, const double* X, long long ldx, long long sX, const doubl
 //                            triangular product on the tensor path instead of a solve recursion to the 128-leaves.
 constexpr int BLK = 512;
 constexpr int PB = 2048;
-__host__ inline long long dinv_elems(long long npad) {
-    return npad * 128 + ((npad + BLK - 1) / BLK) * (long long)BLK * BLK + ((npad + PB - 1) / PB) * (long long)PB * PB;
+__host__ inline long long dinv_elems(long long npad) {   // (no 2048-slots for matrices that are a single panel block)
+    return npad * 128 + ((npad + BLK - 1) / BLK) * (long long)BLK * BLK +
+           (npad > PB ? ((npad + PB - 1) / PB) * (long long)PB * PB : 0);
 }
 struct DinvBuf {
     double* p;

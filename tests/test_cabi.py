@@ -33,9 +33,10 @@ def test_every_declared_symbol_is_exported_and_bound():
     bound = _cabi.load()
     assert bound.plmc_version() >= 100
     assert bound.plmc_npad(44484) == 44544 and bound.plmc_npad(128) == 128
-    # leaf inverses + one dense 512-slot + one 2048-slot for the inverse of the diagonal block
-    assert bound.plmc_dinv_bytes(256, 3) == 3 * (256 * 128 + 512 * 512 + 2048 * 2048) * 8
-    assert bound.plmc_dinv_bytes(1152, 1) == (1152 * 128 + 3 * 512 * 512 + 2048 * 2048) * 8
+    assert bound.plmc_dinv_bytes(256, 3) == 3 * (256 * 128 + 512 * 512) * 8       # leaf inverses + one dense 512-slot
+    assert bound.plmc_dinv_bytes(1152, 1) == (1152 * 128 + 3 * 512 * 512) * 8
+    # above 2048: one 2048-slot per diagonal 2048-block for its explicit inverse (panel solves of potrf)
+    assert bound.plmc_dinv_bytes(4224, 1) == (4224 * 128 + 9 * 512 * 512 + 3 * 2048 * 2048) * 8
 
 
 def test_sass_has_fp64_tensor_core_and_async_copy_instructions():
