@@ -1,6 +1,7 @@
 #include "gemm_dmma.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace plmc {
 
@@ -30,8 +31,10 @@ void stats_reset() {
 
 template <bool A, bool B, bool T>
 static int set_attr() {
-    return cudaFuncSetAttribute(gemm_dmma_kernel<A, B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                G_SMEM_BYTES) == cudaSuccess
+    return (cudaFuncSetAttribute(gemm_dmma_kernel<A, B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 G_SMEM_BYTES) == cudaSuccess &&
+            cudaFuncSetAttribute(gemm_dmma_small_kernel<A, B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 S_SMEM_BYTES) == cudaSuccess)
                ? PLMC_OK
                : PLMC_ERR_LAUNCH;
 }
@@ -61,6 +64,28 @@ static void launch_variant(bool aKC, bool bKC, dim3 grid, cudaStream_t st, const
         gemm_dmma_kernel<false, false, T><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
 }
 
+template <bool T>
+static void launch_small(bool aKC, bool bKC, dim3 grid, cudaStream_t st, const GemmArgs& a) {
+    if (aKC && bKC)
+        gemm_dmma_small_kernel<true, true, T><<<grid, S_THREADS, S_SMEM_BYTES, st>>>(a);
+    else if (aKC && !bKC)
+        gemm_dmma_small_kernel<true, false, T><<<grid, S_THREADS, S_SMEM_BYTES, st>>>(a);
+    else if (!aKC && bKC)
+        gemm_dmma_small_kernel<false, true, T><<<grid, S_THREADS, S_SMEM_BYTES, st>>>(a);
+    else
+        gemm_dmma_small_kernel<false, false, T><<<grid, S_THREADS, S_SMEM_BYTES, st>>>(a);
+}
+
+// diagnostics: PLMC_SMALL_GEMM=0 in the environment keeps every product on the 128 x 128 kernel
+static bool small_gemm_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PLMC_SMALL_GEMM");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 // the >48 KB shared-memory opt-in is a per-device function attribute: done lazily, once per device ordinal
 static bool g_gemm_attr_done[64];
 static int gemm_attrs_for_current_device() {
@@ -87,6 +112,18 @@ int gemm_launch(bool aKC, bool bKC, const GemmArgs& a, int batch, cudaStream_t s
         tiles = tm * tn;
     }
     if (tiles > 2147483647LL || batch > 65535) return PLMC_ERR_BADARG;
+    // fewer 128-tiles than half the SMs: 32 x 128 CTA tiles (four times the SMs); not when C aliases B
+    const long long tiles_full = a.lower ? tiles : tm * tn;
+    if (small_gemm_enabled() && tiles_full * batch <= 74 && a.C != a.B) {
+        dim3 grid_s((unsigned)((a.M / S_BM) * tn), 1, (unsigned)batch);
+        if (a.triA || a.triB)
+            launch_small<true>(aKC, bKC, grid_s, st, a);
+        else
+            launch_small<false>(aKC, bKC, grid_s, st, a);
+        PLMC_CHECK_LAUNCH();
+        note_launch(1, 2.0 * (double)tiles * G_BM * G_BN * (double)a.K * batch);
+        return PLMC_OK;
+    }
     dim3 grid((unsigned)tiles, 1, (unsigned)batch);
     if (a.triA || a.triB)
         launch_variant<true>(aKC, bKC, grid, st, a);
