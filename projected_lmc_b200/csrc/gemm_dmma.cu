@@ -85,6 +85,16 @@ static bool small_gemm_enabled() {
     }
     return v == 1;
 }
+// products of at most this many 128-tiles (over the batch) take the 32 x 128 kernel (PLMC_SMALL_GEMM_TILES)
+static long long small_gemm_tiles() {
+    static long long v = -1;
+    if (v < 0) {
+        const char* e = getenv("PLMC_SMALL_GEMM_TILES");
+        v = e ? atoll(e) : 296;
+        if (v < 0) v = 0;
+    }
+    return v;
+}
 
 // the >48 KB shared-memory opt-in is a per-device function attribute: done lazily, once per device ordinal
 static bool g_gemm_attr_done[64];
@@ -112,9 +122,9 @@ int gemm_launch(bool aKC, bool bKC, const GemmArgs& a, int batch, cudaStream_t s
         tiles = tm * tn;
     }
     if (tiles > 2147483647LL || batch > 65535) return PLMC_ERR_BADARG;
-    // fewer 128-tiles than half the SMs: 32 x 128 CTA tiles (four times the SMs); not when C aliases B
+    // at most two waves of 128-tiles: 32 x 128 CTA tiles (four times the CTAs, two per SM); not when C aliases B
     const long long tiles_full = a.lower ? tiles : tm * tn;
-    if (small_gemm_enabled() && tiles_full * batch <= 74 && a.C != a.B) {
+    if (small_gemm_enabled() && tiles_full * batch <= small_gemm_tiles() && a.C != a.B) {
         dim3 grid_s((unsigned)((a.M / S_BM) * tn), 1, (unsigned)batch);
         if (a.triA || a.triB)
             launch_small<true>(aKC, bKC, grid_s, st, a);
