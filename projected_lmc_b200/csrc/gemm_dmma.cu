@@ -33,7 +33,9 @@ template <bool A, bool B, bool T>
 static int set_attr() {
     return (cudaFuncSetAttribute(gemm_dmma_kernel<A, B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  G_SMEM_BYTES) == cudaSuccess &&
-            cudaFuncSetAttribute(gemm_dmma_small_kernel<A, B, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaFuncSetAttribute(gemm_dmma_small_kernel<A, B, T, 32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 S_SMEM_BYTES) == cudaSuccess &&
+            cudaFuncSetAttribute(gemm_dmma_small_kernel<A, B, T, 128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  S_SMEM_BYTES) == cudaSuccess)
                ? PLMC_OK
                : PLMC_ERR_LAUNCH;
@@ -64,16 +66,16 @@ static void launch_variant(bool aKC, bool bKC, dim3 grid, cudaStream_t st, const
         gemm_dmma_kernel<false, false, T><<<grid, G_THREADS, G_SMEM_BYTES, st>>>(a);
 }
 
-template <bool T>
+template <bool T, int TM, int TN>
 static void launch_small(bool aKC, bool bKC, dim3 grid, cudaStream_t st, const GemmArgs& a) {
     if (aKC && bKC)
-        gemm_dmma_small_kernel<true, true, T><<<grid, S_THREADS, S_SMEM_BYTES, st>>>(a);
+        gemm_dmma_small_kernel<true, true, T, TM, TN><<<grid, S_THREADS, S_SMEM_BYTES, st>>>(a);
     else if (aKC && !bKC)
-        gemm_dmma_small_kernel<true, false, T><<<grid, S_THREADS, S_SMEM_BYTES, st>>>(a);
+        gemm_dmma_small_kernel<true, false, T, TM, TN><<<grid, S_THREADS, S_SMEM_BYTES, st>>>(a);
     else if (!aKC && bKC)
-        gemm_dmma_small_kernel<false, true, T><<<grid, S_THREADS, S_SMEM_BYTES, st>>>(a);
+        gemm_dmma_small_kernel<false, true, T, TM, TN><<<grid, S_THREADS, S_SMEM_BYTES, st>>>(a);
     else
-        gemm_dmma_small_kernel<false, false, T><<<grid, S_THREADS, S_SMEM_BYTES, st>>>(a);
+        gemm_dmma_small_kernel<false, false, T, TM, TN><<<grid, S_THREADS, S_SMEM_BYTES, st>>>(a);
 }
 
 // diagnostics: PLMC_SMALL_GEMM=0 in the environment keeps every product on the 128 x 128 kernel
@@ -122,14 +124,22 @@ int gemm_launch(bool aKC, bool bKC, const GemmArgs& a, int batch, cudaStream_t s
         tiles = tm * tn;
     }
     if (tiles > 2147483647LL || batch > 65535) return PLMC_ERR_BADARG;
-    // at most two waves of 128-tiles: 32 x 128 CTA tiles (four times the CTAs, two per SM); not when C aliases B
+    // at most two waves of 128-tiles: 32 x 128 CTA tiles (four times the CTAs, two per SM); when C aliases B (M = K =
+    // 128: the leaves of the left-sided solves / multiplies) the transposed tiling 128 x 32, whose CTAs read only
+    // their own columns of B
     const long long tiles_full = a.lower ? tiles : tm * tn;
-    if (small_gemm_enabled() && tiles_full * batch <= small_gemm_tiles() && a.C != a.B) {
-        dim3 grid_s((unsigned)((a.M / S_BM) * tn), 1, (unsigned)batch);
-        if (a.triA || a.triB)
-            launch_small<true>(aKC, bKC, grid_s, st, a);
-        else
-            launch_small<false>(aKC, bKC, grid_s, st, a);
+    const bool alias_b = (a.C == a.B);
+    if (small_gemm_enabled() && tiles_full * batch <= small_gemm_tiles() && (!alias_b || (a.M == 128 && a.C != a.A))) {
+        const bool tri = a.triA || a.triB;
+        if (!alias_b) {
+            dim3 grid_s((unsigned)((a.M / 32) * tn), 1, (unsigned)batch);
+            if (tri) launch_small<true, 32, 128>(aKC, bKC, grid_s, st, a);
+            else launch_small<false, 32, 128>(aKC, bKC, grid_s, st, a);
+        } else {
+            dim3 grid_s((unsigned)(tm * (a.N / 32)), 1, (unsigned)batch);
+            if (tri) launch_small<true, 128, 32>(aKC, bKC, grid_s, st, a);
+            else launch_small<false, 128, 32>(aKC, bKC, grid_s, st, a);
+        }
         PLMC_CHECK_LAUNCH();
         note_launch(1, 2.0 * (double)tiles * G_BM * G_BN * (double)a.K * batch);
         return PLMC_OK;

@@ -343,34 +343,27 @@ __global__ void __launch_bounds__(G_THREADS, 1) gemm_dmma_kernel(const GemmArgs 
 // iteration, most of them a handful of 128-tiles.  With 128 x 128 CTA tiles such a launch occupies 4-60 SMs for the
 // 17 us one SM needs for a 128^3 tile on its FP64 tensor pipe.  This variant cuts the same product into 32 x 128 CTA
 // tiles (4 warps, warp tile 32 x 32): four times as many SMs, a quarter of the time.  A CTA reads only ITS 32 rows of
-// op(A), so C may alias A under the same condition as above (K a single 128-tile); C must not alias B.
+// op(A), so C may alias A under the same condition as above (K a single 128-tile).  The transposed tiling, 128 x 32,
+// reads only ITS 32 columns of op(B) and all of op(A): it serves the products in which C aliases B (M = K = 128).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int S_BM = 32, S_BN = 128, S_BK = 32, S_THREADS = 128, S_STAGES = 2;
+constexpr int S_BK = 32, S_THREADS = 128, S_STAGES = 2;
 constexpr int S_LDK = S_BK + 4;       // k-contiguous tiles: [rows][36]
-constexpr int S_LDA = S_BM + 4;       // m-contiguous A tile: [32 k][36]
-constexpr int S_LDN = S_BN + 4;       // n-contiguous B tile: [32 k][132]
-constexpr int S_ATILE = (S_BM * S_LDK > S_BK * S_LDA) ? S_BM * S_LDK : S_BK * S_LDA;
-constexpr int S_BTILE = (S_BN * S_LDK > S_BK * S_LDN) ? S_BN * S_LDK : S_BK * S_LDN;
-constexpr int S_STAGE = S_ATILE + S_BTILE;
-constexpr int S_SMEM_BYTES = S_STAGES * S_STAGE * 8;
+template <int TM, int TN>
+struct SmallCfg {                     // CTA tile TM x TN: 32 x 128 (C may alias A) or 128 x 32 (C may alias B)
+    static constexpr int LDA = TM + 4, LDN = TN + 4;   // m- / n-contiguous tiles: [32 k][TM + 4], [32 k][TN + 4]
+    static constexpr int ATILE = (TM * S_LDK > S_BK * LDA) ? TM * S_LDK : S_BK * LDA;
+    static constexpr int BTILE = (TN * S_LDK > S_BK * LDN) ? TN * S_LDK : S_BK * LDN;
+    static constexpr int STAGE = ATILE + BTILE;
+    static constexpr int SMEM_BYTES = S_STAGES * STAGE * 8;
+};
+constexpr int S_SMEM_BYTES = SmallCfg<32, 128>::SMEM_BYTES;   // = SmallCfg<128, 32>::SMEM_BYTES
 
-template <bool A_KC, bool B_KC, bool TRI>
-__global__ void __launch_bounds__(S_THREADS, 2) gemm_dmma_small_kernel(const GemmArgs p) {
-    extern __shared__ __align__(16) double smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int rows32 = p.M / S_BM;
-    const int ti = blockIdx.x % rows32, tj = blockIdx.x / rows32;
-    const int m0 = ti * S_BM, n0 = tj * S_BN;
-    if (p.lower && (m0 >> 7) < tj) return;            // only 128-tiles on or below the diagonal (uniform per CTA)
-
-    const double* __restrict__ A = p.A + (long long)blockIdx.z * p.sA;
-    const double* __restrict__ B = p.B + (long long)blockIdx.z * p.sB;
-    double* __restrict__ C = p.C + (long long)blockIdx.z * p.sC;
-    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(smem);
-    const bool maskA = TRI && p.triA, maskB = TRI && p.triB;
-
-    auto piece = [&](uint32_t dst, const double* src, int r, int c, bool mask) {
+// one operand tile of R rows (R = TM for A, TN for B) and 32 k: 16-byte pieces, zero-filled above the diagonal of a
+// triangular operand.  KC: element (x, k) at P[(x0+x) ld + k] -> tile[x][36];  MC: at P[k ld + x0+x] -> tile[k][R+4]
+template <int R, bool KC, bool TRI>
+__device__ __forceinline__ void small_tile_load(uint32_t sdst, const double* __restrict__ P, long long ld, int x0, int k0,
+                                                int tid, bool mask) {
+    auto piece = [&](uint32_t dst, const double* src, int r, int c) {
         int bytes = 16;
         if (TRI && mask) {
             int v = r - c + 1;
@@ -379,41 +372,49 @@ __global__ void __launch_bounds__(S_THREADS, 2) gemm_dmma_small_kernel(const Gem
         }
         cp_async16s(dst, src, bytes);
     };
-    auto issue = [&](int kt) {
-        const uint32_t sa = sm0 + (uint32_t)(kt & 1) * (S_STAGE * 8u), sb = sa + S_ATILE * 8u;
-        const int k0 = kt * S_BK;
+    if (KC) {
         const int ch = tid & 15, rr = tid >> 4;        // 16 pieces per 32-wide row, 8 rows per pass
-        if (A_KC) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = rr + 8 * i;
-                piece(sa + (uint32_t)(row * S_LDK + ch * 2) * 8u, A + (long long)(m0 + row) * p.lda + k0 + ch * 2,
-                      m0 + row, k0 + ch * 2, maskA);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int krow = rr + 8 * i;
-                piece(sa + (uint32_t)(krow * S_LDA + ch * 2) * 8u, A + (long long)(k0 + krow) * p.lda + m0 + ch * 2,
-                      k0 + krow, m0 + ch * 2, maskA);
-            }
+        for (int i = 0; i < R / 8; ++i) {
+            const int row = rr + 8 * i;
+            piece(sdst + (uint32_t)(row * S_LDK + ch * 2) * 8u, P + (long long)(x0 + row) * ld + k0 + ch * 2, x0 + row,
+                  k0 + ch * 2);
         }
-        if (B_KC) {
+    } else {
+        constexpr int PPR = R / 2;                     // pieces per k-row
+        constexpr int RPP = S_THREADS / PPR;           // k-rows per pass
+        const int ch = tid % PPR, rr = tid / PPR;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int nrow = rr + 8 * i;
-                piece(sb + (uint32_t)(nrow * S_LDK + ch * 2) * 8u, B + (long long)(n0 + nrow) * p.ldb + k0 + ch * 2,
-                      n0 + nrow, k0 + ch * 2, maskB);
-            }
-        } else {
-            const int ch6 = tid & 63, r2 = tid >> 6;   // 64 pieces per 128-wide row, 2 rows per pass
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int krow = r2 + 2 * i;
-                piece(sb + (uint32_t)(krow * S_LDN + ch6 * 2) * 8u, B + (long long)(k0 + krow) * p.ldb + n0 + ch6 * 2,
-                      k0 + krow, n0 + ch6 * 2, maskB);
-            }
+        for (int i = 0; i < S_BK / RPP; ++i) {
+            const int krow = rr + RPP * i;
+            piece(sdst + (uint32_t)(krow * (R + 4) + ch * 2) * 8u, P + (long long)(k0 + krow) * ld + x0 + ch * 2, k0 + krow,
+                  x0 + ch * 2);
         }
+    }
+}
+
+template <bool A_KC, bool B_KC, bool TRI, int TM, int TN>
+__global__ void __launch_bounds__(S_THREADS, 2) gemm_dmma_small_kernel(const GemmArgs p) {
+    using SC = SmallCfg<TM, TN>;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm0 = (TM == 128) ? warp * 32 : 0, wn0 = (TN == 128) ? warp * 32 : 0;   // warp tile 32 x 32
+    const int tiles_m = p.M / TM;
+    const int ti = blockIdx.x % tiles_m, tj = blockIdx.x / tiles_m;
+    const int m0 = ti * TM, n0 = tj * TN;
+    if (p.lower && (m0 >> 7) < (n0 >> 7)) return;     // only 128-tiles on or below the diagonal (uniform per CTA)
+
+    const double* __restrict__ A = p.A + (long long)blockIdx.z * p.sA;
+    const double* __restrict__ B = p.B + (long long)blockIdx.z * p.sB;
+    double* __restrict__ C = p.C + (long long)blockIdx.z * p.sC;
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(smem);
+    const bool maskA = TRI && p.triA, maskB = TRI && p.triB;
+
+    auto issue = [&](int kt) {
+        const uint32_t sa = sm0 + (uint32_t)(kt & 1) * (SC::STAGE * 8u), sb = sa + SC::ATILE * 8u;
+        small_tile_load<TM, A_KC, TRI>(sa, A, p.lda, m0, kt * S_BK, tid, maskA);
+        small_tile_load<TN, B_KC, TRI>(sb, B, p.ldb, n0, kt * S_BK, tid, maskB);
     };
 
     double acc[4][4][2];
@@ -430,17 +431,17 @@ __global__ void __launch_bounds__(S_THREADS, 2) gemm_dmma_small_kernel(const Gem
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const double* sa = smem + (kt & 1) * S_STAGE;
-        const double* sb = sa + S_ATILE;
-        const double* pa = A_KC ? sa + g * S_LDK + t : sa + t * S_LDA + g;
-        const double* pb = B_KC ? sb + (warp * 32 + g) * S_LDK + t : sb + t * S_LDN + warp * 32 + g;
+        const double* sa = smem + (kt & 1) * SC::STAGE;
+        const double* sb = sa + SC::ATILE;
+        const double* pa = A_KC ? sa + (wm0 + g) * S_LDK + t : sa + t * SC::LDA + wm0 + g;
+        const double* pb = B_KC ? sb + (wn0 + g) * S_LDK + t : sb + t * SC::LDN + wn0 + g;
 #pragma unroll
         for (int kk = 0; kk < S_BK / 4; ++kk) {
             double af[4], bf[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = A_KC ? pa[i * 8 * S_LDK + kk * 4] : pa[kk * 4 * S_LDA + i * 8];
+            for (int i = 0; i < 4; ++i) af[i] = A_KC ? pa[i * 8 * S_LDK + kk * 4] : pa[kk * 4 * SC::LDA + i * 8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = B_KC ? pb[j * 8 * S_LDK + kk * 4] : pb[kk * 4 * S_LDN + j * 8];
+            for (int j = 0; j < 4; ++j) bf[j] = B_KC ? pb[j * 8 * S_LDK + kk * 4] : pb[kk * 4 * SC::LDN + j * 8];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -455,7 +456,8 @@ __global__ void __launch_bounds__(S_THREADS, 2) gemm_dmma_small_kernel(const Gem
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            double2* cp = reinterpret_cast<double2*>(C + (long long)(m0 + i * 8 + g) * p.ldc + (n0 + warp * 32 + j * 8 + 2 * t));
+            double2* cp =
+                reinterpret_cast<double2*>(C + (long long)(m0 + wm0 + i * 8 + g) * p.ldc + (n0 + wn0 + j * 8 + 2 * t));
             double2 o = make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
             if (beta != 0.0) {
                 const double2 c = *cp;
