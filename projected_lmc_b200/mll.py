@@ -75,14 +75,15 @@ class ProjectedLMCmll(gp.mlls.ExactMarginalLogLikelihood):
             raise RuntimeError("ExactMarginalLogLikelihood can only operate on Gaussian random variables")
         model = self.model
         num_data = latent_function_dist.event_shape.numel()
-        proj_target = model.project_data(target)                          # n_latents x n_points
-        latent_output = self.likelihood(latent_function_dist, *params)
-        latent_res = latent_output.log_prob(proj_target)                  # latents owned by this process
-        latent_res = self._add_other_terms(latent_res, params).sum().div(num_data)
+        with model.lmc_coefficients.qr_once():                            # one QR of H for both of its uses
+            proj_target = model.project_data(target)                      # n_latents x n_points
+            latent_output = self.likelihood(latent_function_dist, *params)
+            latent_res = latent_output.log_prob(proj_target)              # latents owned by this process
+            latent_res = self._add_other_terms(latent_res, params).sum().div(num_data)
 
-        p, q = model.n_tasks, model.n_latents
-        S = self._second_moment(target).to(proj_target.dtype)
-        self.proj_term_list = list(projection_terms(model, S, num_data))
+            p, q = model.n_tasks, model.n_latents
+            S = self._second_moment(target).to(proj_target.dtype)
+            self.proj_term_list = list(projection_terms(model, S, num_data))
         projection_term = sum(self.proj_term_list) - 0.5 * (p - q) * np.log(2 * np.pi)
         world = getattr(model, "_world_size", 1)
         # latent-parallel runs: every rank carries 1/world of the shared terms so that the

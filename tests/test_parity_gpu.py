@@ -333,6 +333,29 @@ def test_fit_falls_back_to_eager_launches_when_the_step_cannot_be_captured():
     assert torch.isfinite(torch.randn(4, device="cuda")).all()
 
 
+@pytest.mark.parametrize("variant", ["PLMC", "PLMC_fast"])
+def test_one_shared_qr_per_loss_evaluation_gives_the_gradients_of_two(variant):
+    """ProjectedLMCmll.forward factorises H once for project_data and the projection terms (qr_once); the reference
+    factorises twice.  Same loss bits, gradients equal to rounding."""
+    import contextlib
+
+    X, Y, _, _ = synth(400, 3, 6, 2, seed=21)
+    m = make_model(X, Y, 2, variant=variant, kernel="matern52").cuda()
+    Xg, Yg = X.cuda(), Y.cuda()
+    res = []
+    for shared in (True, False):
+        if not shared:
+            m.lmc_coefficients.qr_once = contextlib.nullcontext          # two factorisations, as in the reference
+        for p in m.parameters():
+            p.grad = None
+        loss = -ProjectedLMCmll(m.likelihood, m)(m(Xg), Yg)
+        loss.backward()
+        res.append((loss.item(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    assert abs(res[0][0] - res[1][0]) <= 1e-14 * abs(res[1][0])
+    for k in res[0][1]:
+        assert rel_err(res[0][1][k], res[1][1][k]) < 1e-12, k
+
+
 def test_fit_plateau_stop_rule():
     from projected_lmc_b200 import fit
 
