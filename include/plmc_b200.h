@@ -191,7 +191,8 @@ int plmc_potri_batched(double* L, long long ld, long long stride, long long npad
  * (experiments.py:270 loss.backward()).  With W = 1/2 (alpha alpha^T - K^-1):
  *   g_noise[l] = tr W ; g_os[l] = sum W o k ; g_ell[l,k] = d lp / d ell[l,k].
  * Kinv: lower tiles of K^-1; Z, zn: scaled inputs and their squared norms (plmc_scale_inputs); partial: workspace
- * of plmc_grad_ws(...) bytes.  d <= 24: both contractions (distances, A Z) on the FP64 tensor cores.             */
+ * of plmc_grad_ws(...) bytes.  d <= 24: both contractions (distances, A Z) on the FP64 tensor cores; 24 < d <= 44:
+ * direct-difference kernel; wider inputs: PLMC_ERR_BADARG (split the kernel into additive `decomp` groups).      */
 long long plmc_grad_ws(long long npad, int d, int q);
 /* diagnostics (process-wide, like plmc_trace_enable): direct != 0 forces the direct-difference sweep kernel that
  * otherwise only serves inputs of more than 24 dimensions; 0 restores the default (GEMM form on DMMA for d <= 24) */
