@@ -39,6 +39,15 @@ def test_roofline_entry_residue_scheme_uses_the_measured_int8_peak():
     assert "rns_gemm_kernel" in r["kernel"] and "plmc_peak_i8" in r["peak_source"]
 
 
+def test_roofline_entry_of_a_long_step_uses_the_sustained_int8_rate_and_keeps_the_burst_beside_it():
+    r = bench.roofline_entry(_eng("rns", rns_moduli=15, rns_moduli_kinv=12), 120.0, 37.0, {"bf16_tflops_sustained": 1408.0},
+                             "MEASURED_PEAKS.json", 1e12, 100, 1000.0, 1, i8_peak=4300.0, i8_sustained=3700.0)
+    assert r["int8_products_per_fp64_product"] == 13.0
+    assert abs(r["peak"] - 3700.0 / 13.0) < 1e-9 and abs(r["frac"] - 120.0 / r["peak"]) < 1e-12
+    assert abs(r["peak_burst"] - 4300.0 / 13.0) < 1e-9 and abs(r["frac_of_burst_peak"] - 120.0 / r["peak_burst"]) < 1e-12
+    assert "sustained" in r["peak_source"] and r["traffic"] > 0
+
+
 def test_roofline_entry_pure_fp64_mode_is_measured_against_the_dmma_peak():
     r = bench.roofline_entry(_eng("fp64"), 32.0, 37.0, {}, "fallback", 1e12, 100, 1000.0, 1)
     assert r["peak"] == 37.0 and abs(r["frac"] - 32.0 / 37.0) < 1e-12
