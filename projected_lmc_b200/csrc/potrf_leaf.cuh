@@ -24,13 +24,38 @@ constexpr int LEAF = 128;
 constexpr int LF_LD = 132;
 constexpr int LEAF_THREADS = 256;
 constexpr int LF_NB = 16;
-constexpr int LEAF_SMEM = LEAF * LF_LD * 8 + 16;
+constexpr int LEAF_SMEM = LEAF * LF_LD * 8 + 16 + LEAF * 8;   // matrix, failure flag, reciprocals of the diagonal
+
+// sqrt(s) and 1/sqrt(s) from ONE coupled Goldschmidt iteration (MUFU.RSQ64H seed, as csrc/kernel_math.cuh sqrt_pos:
+// root to <= 1 ulp, reciprocal to <= 2 ulp), ~70 cycles of dependent FP64 work.  The library sqrt() followed by a
+// division is ~350 cycles, and it sits on the one chain of the whole factorisation that nothing can overlap: the
+// pivot of column c+1 needs the scaled column c (ncu: 53 % of the leaf's time was the 16 x 16 diagonal block
+// factorisation, seven of eight warps waiting at its barrier).  s <= 0 or NaN gives NaN for both, like sqrt().
+__device__ __forceinline__ void sqrt_and_reciprocal(double s, double& root, double& inv) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+    double g = s * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double d = fma(-g, g, s);                 // residual: g <- g + d / (2 g)
+    g = fma(d, h, g);
+    r = fma(-h, g, 0.5);                            // h <- 1 / (2 g) for the corrected root
+    h = fma(h, r, h);
+    const bool ok = s > 0.0;
+    root = ok ? g : __longlong_as_double(0x7ff8000000000000LL);
+    inv = ok ? h + h : __longlong_as_double(0x7ff8000000000000LL);
+}
 
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
     potrf_leaf_kernel(double* __restrict__ Abase, long long ld, long long sA, double* __restrict__ Dbase,
                       long long sD, int* __restrict__ info, int row_off) {
     extern __shared__ __align__(16) double S[];
     int* fail_sh = reinterpret_cast<int*>(S + LEAF * LF_LD);
+    double* rdiag = S + LEAF * LF_LD + 2;            // 1 / L_kk, written by the diagonal-block warp
     const int b = blockIdx.x;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -59,8 +84,9 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1)
             for (int c = 0; c < LF_NB; ++c) {
                 const double d = __shfl_sync(0xffffffffu, a[c], c);
                 if (!(d > 0.0) && bad == 0) bad = j0 + c + 1;
-                const double l = sqrt(d);
-                const double inv = 1.0 / l;
+                double l, inv;
+                sqrt_and_reciprocal(d, l, inv);
+                if (lane == 0) rdiag[j0 + c] = inv;
                 a[c] = (r == c) ? l : a[c] * inv;
 #pragma unroll
                 for (int cc = c + 1; cc < LF_NB; ++cc) {
@@ -90,7 +116,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1)
                 double s = x[c];
 #pragma unroll
                 for (int k = 0; k < c; ++k) s = fma(-x[k], lrow[k], s);
-                x[c] = s / lrow[c];
+                x[c] = s * rdiag[j0 + c];
             }
 #pragma unroll
             for (int c = 0; c < LF_NB; ++c) row[c] = x[c];
@@ -141,7 +167,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1)
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 if (k < i) s = fma(-l[i][k], (k >= j) ? x[k] : 0.0, s);
-            x[i] = (i >= j) ? s / l[i][i] : 0.0;
+            x[i] = (i >= j) ? s * rdiag[blk * 8 + i] : 0.0;
         }
         __syncwarp();  // all 8 columns of a block live in one warp: reads above are done
 #pragma unroll
