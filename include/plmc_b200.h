@@ -119,6 +119,9 @@ int plmc_project_bwd(const double* Y, const double* G, long long ldg, double* dT
 /* host-only helper (HOST pointers, no device work): k(s) and dk/ds of PLMC_KERNEL_* evaluated by the same source
  * the device kernels compile (csrc/kernel_math.cuh: hand-written exp / sqrt), for CPU-side accuracy tests. */
 int plmc_kernel_profile_host(int kernel_id, const double* s_host, long long n, double* k_host, double* dk_host);
+/* host-only helper: sqrt(s) and 1/sqrt(s) as the Cholesky leaf computes its pivots (one coupled Goldschmidt
+ * iteration, csrc/kernel_math.cuh), for CPU-side accuracy tests; s <= 0 gives NaN for both. */
+int plmc_sqrt_reciprocal_host(const double* s_host, long long n, double* root_host, double* inv_host);
 /* xmean[k] = mean_i X[i,k] */
 int plmc_col_mean(const double* X, long long n, int d, double* xmean, void* stream);
 /* Z[l, i, k] = (X[i,k]-xmean[k]) / ell[l,k], zero padded to [q, rows_pad, dpad];

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "plmc_project_bwd_ws": [LL, I, I],
     "plmc_project_bwd": [P, P, LL, P, P, LL, I, I, P],
     "plmc_kernel_profile_host": [I, P, LL, P, P],
+    "plmc_sqrt_reciprocal_host": [P, LL, P, P],
     "plmc_col_mean": [P, LL, I, P, P],
     "plmc_scale_inputs": [P, P, P, P, P, LL, I, I, LL, I, P],
     "plmc_gram": [P, P, I, P, P, P, LL, LL, LL, LL, I, I, I, P],

@@ -697,6 +697,13 @@ int plmc_kernel_profile_host(int kernel_id, const double* s_host, long long n, d
     return PLMC_OK;
 }
 
+/* host only: the pivot step of the Cholesky leaf (csrc/kernel_math.cuh sqrt_and_reciprocal) on host arrays */
+int plmc_sqrt_reciprocal_host(const double* s_host, long long n, double* root_host, double* inv_host) {
+    if (!s_host || !root_host || !inv_host || n < 0) return PLMC_ERR_BADARG;
+    for (long long i = 0; i < n; ++i) sqrt_and_reciprocal(s_host[i], root_host[i], inv_host[i]);
+    return PLMC_OK;
+}
+
 int plmc_col_mean(const double* X, long long n, int d, double* xmean, void* stream) {
     if (!X || !xmean || n <= 0 || d <= 0) return PLMC_ERR_BADARG;
     col_mean_kernel<<<d, 256, 0, (cudaStream_t)stream>>>(X, n, d, xmean);

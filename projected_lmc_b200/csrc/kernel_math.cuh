@@ -96,6 +96,38 @@ __host__ __device__ __forceinline__ double sqrt_pos(double s) {
     return fma(d, h, g);
 }
 
+// sqrt(s) and 1/sqrt(s) from ONE coupled Goldschmidt iteration (the Cholesky leaf's pivot step, csrc/potrf_leaf.cuh):
+// root to <= 1 ulp, reciprocal to <= 2 ulp (checked on the host by tests/test_kernel_math_cpu.py).  s <= 0 or NaN
+// gives NaN for both, like sqrt() of a negative number.
+__host__ __device__ __forceinline__ void sqrt_and_reciprocal(double s, double& root, double& inv) {
+    double y;
+#ifdef __CUDA_ARCH__
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+#else
+    y = (double)(1.0f / sqrtf((float)s));
+    if (!(y > 0.0) || y > 1e30) y = 1.0 / sqrt(s);           // outside float range (host test only)
+#endif
+    double g = s * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double d = fma(-g, g, s);                          // residual: g <- g + d / (2 g)
+    g = fma(d, h, g);
+    r = fma(-h, g, 0.5);                                     // h <- 1 / (2 g) for the corrected root
+    h = fma(h, r, h);
+    const bool ok = s > 0.0;
+#ifdef __CUDA_ARCH__
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#else
+    const double qnan = NAN;
+#endif
+    root = ok ? g : qnan;
+    inv = ok ? h + h : qnan;
+}
+
 template <int KID>
 __host__ __device__ __forceinline__ double kernel_value(double s) {
     if (KID == 0) return exp_nonpos(-0.5 * s);

@@ -16,7 +16,7 @@
 // Shared row stride 132 doubles makes row- and column-direction fragment reads
 // bank-conflict free.
 #pragma once
-#include "plmc_common.cuh"
+#include "kernel_math.cuh"
 
 namespace plmc {
 
@@ -26,29 +26,10 @@ constexpr int LEAF_THREADS = 256;
 constexpr int LF_NB = 16;
 constexpr int LEAF_SMEM = LEAF * LF_LD * 8 + 16 + LEAF * 8;   // matrix, failure flag, reciprocals of the diagonal
 
-// sqrt(s) and 1/sqrt(s) from ONE coupled Goldschmidt iteration (MUFU.RSQ64H seed, as csrc/kernel_math.cuh sqrt_pos:
-// root to <= 1 ulp, reciprocal to <= 2 ulp), ~70 cycles of dependent FP64 work.  The library sqrt() followed by a
-// division is ~350 cycles, and it sits on the one chain of the whole factorisation that nothing can overlap: the
-// pivot of column c+1 needs the scaled column c (ncu: 53 % of the leaf's time was the 16 x 16 diagonal block
-// factorisation, seven of eight warps waiting at its barrier).  s <= 0 or NaN gives NaN for both, like sqrt().
-__device__ __forceinline__ void sqrt_and_reciprocal(double s, double& root, double& inv) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
-    double g = s * y, h = 0.5 * y;
-    double r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    const double d = fma(-g, g, s);                 // residual: g <- g + d / (2 g)
-    g = fma(d, h, g);
-    r = fma(-h, g, 0.5);                            // h <- 1 / (2 g) for the corrected root
-    h = fma(h, r, h);
-    const bool ok = s > 0.0;
-    root = ok ? g : __longlong_as_double(0x7ff8000000000000LL);
-    inv = ok ? h + h : __longlong_as_double(0x7ff8000000000000LL);
-}
+// sqrt_and_reciprocal (csrc/kernel_math.cuh): pivot root and reciprocal from ONE coupled Goldschmidt iteration, ~70
+// cycles of dependent FP64 work.  The library sqrt() followed by a division is ~350 cycles, and it sits on the one
+// chain of the whole factorisation that nothing can overlap: the pivot of column c+1 needs the scaled column c (ncu: 53 %
+// of the leaf's time was the 16 x 16 diagonal block factorisation, seven of eight warps waiting at its barrier).
 
 __global__ void __launch_bounds__(LEAF_THREADS, 1)
     potrf_leaf_kernel(double* __restrict__ Abase, long long ld, long long sA, double* __restrict__ Dbase,

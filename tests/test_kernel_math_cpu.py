@@ -74,3 +74,21 @@ def test_profile_at_zero_distance_and_monotonicity():
         assert np.all(np.diff(k) <= 0) and np.all(dk[1:] <= 0)
     k, _ = profile(0, np.array([5000.0, 1e300]))
     assert k[0] == 0.0 and k[1] == 0.0
+
+
+def test_pivot_root_and_reciprocal_of_the_cholesky_leaf_within_one_and_two_ulps():
+    """sqrt_and_reciprocal (one coupled Goldschmidt iteration; the pivot step of potrf_leaf_kernel): root <= 1 ulp,
+    reciprocal <= 2 ulp over twelve decades; non-positive pivots give NaN like sqrt()."""
+    lib = _cabi.load()
+    rng = np.random.default_rng(5)
+    s = np.concatenate([10.0 ** rng.uniform(-6, 6, 200000), rng.uniform(0.5, 2.0, 100000), [1.0, 4.0, 0.25, 2.0, 1e-300, 1e300]])
+    root, inv = np.empty_like(s), np.empty_like(s)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert lib.plmc_sqrt_reciprocal_host(vp(s), s.size, vp(root), vp(inv)) == 0
+    sl = s.astype(np.longdouble)
+    assert ulps(root, np.sqrt(sl)).max() <= 1.0
+    assert ulps(inv, 1 / np.sqrt(sl)).max() <= 2.0
+    bad = np.array([0.0, -1.0, np.nan])
+    r2, i2 = np.empty_like(bad), np.empty_like(bad)
+    assert lib.plmc_sqrt_reciprocal_host(vp(bad), bad.size, vp(r2), vp(i2)) == 0
+    assert np.isnan(r2).all() and np.isnan(i2).all()
